@@ -1,0 +1,54 @@
+// acs_internal.h -- declarations shared by the translation units of libacsolver_b200.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace acs {
+
+// Arguments of the batched move / env-step kernels (moves_kernel.cu).
+struct StepParams {
+    const int8_t* in;       // [n, 2*mrl]
+    int8_t* out;            // [n, 2*mrl], may alias in
+    const uint8_t* action;  // [n]
+    uint8_t* lens;          // [n,2] or null
+    uint8_t* status;        // [n] or null
+    unsigned long long* err;  // {count, min row} or null
+    int32_t* reward;        // [n] or null  (null => plain ACMove, no env bookkeeping)
+    uint8_t* done;          // [n]
+    uint8_t* truncated;     // [n]
+    int32_t* step_count;    // [n] in/out
+    int64_t n;
+    int mrl;
+    int cyclical;
+    int horizon;
+    int max_reward;
+    int bulk_ok;            // in/out are 16-byte aligned: TMA bulk copies allowed
+};
+
+cudaError_t launch_step(const StepParams& P, cudaStream_t s);
+
+// byte-domain reference-semantics kernel for any int8 alphabet (generic_kernel.cu)
+enum GenericOp : int {
+    OP_ACMOVE = 0,
+    OP_CONCAT_RAW = 1,
+    OP_CONJ_RAW = 2,
+    OP_SIMPLIFY_RELATOR = 3,
+    OP_SIMPLIFY_PRESENTATION = 4,
+};
+struct GenericParams {
+    int op;
+    const int8_t* in;       // [n, width]
+    const uint8_t* action;  // [n] (OP_ACMOVE)
+    int8_t* out;            // [n, width]
+    int32_t* aux;           // OP_ACMOVE / SIMPLIFY_PRESENTATION: [n,2] lengths; RAW: [n] new size or -1/-2;
+                            // SIMPLIFY_RELATOR: [n] length
+    uint8_t* status;        // [n]
+    int64_t n;
+    int width;              // letters per row (2*mrl, or the relator width for SIMPLIFY_RELATOR)
+    int i, j, sign;         // RAW ops
+    int cyclical;
+};
+cudaError_t launch_generic(const GenericParams& P, cudaStream_t s);
+cudaError_t launch_validate(const int8_t* in, uint8_t* flags, int64_t n, int mrl, cudaStream_t s);
+
+}  // namespace acs

@@ -1,0 +1,319 @@
+// capi.cu -- the C ABI of libacsolver_b200.so (see include/acsolver_b200.h).
+// Host-side runtime only: argument checks, the context (streams + grow-only scratch) and
+// the chunked H2D -> kernel -> D2H pipelines behind the *_host entry points.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include <cuda_runtime.h>
+
+#include "../../include/acsolver_b200.h"
+#include "acs_internal.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* what) {
+    g_err = what ? what : "";
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? ACS_ERR_NOMEM : ACS_ERR_CUDA;
+}
+#define ACS_CUDA(call)                                          \
+    do {                                                        \
+        cudaError_t e__ = (call);                               \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);   \
+    } while (0)
+
+constexpr int kStreams = 3;
+constexpr int64_t kChunkRows = 1 << 17;  // rows per pipeline chunk of the *_host calls
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return ACS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(scratch)");
+        cap = bytes;
+        return ACS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct acs_ctx {
+    int device = 0;
+    cudaStream_t streams[kStreams] = {};
+    Scratch scratch[kStreams];
+    unsigned long long* d_err = nullptr;  // {count, min row}
+    unsigned long long* h_err = nullptr;  // pinned mirror
+};
+
+extern "C" {
+
+int acs_version(void) { return 100; }
+const char* acs_last_error(void) { return g_err.c_str(); }
+
+int acs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int acs_ctx_create(int device, acs_ctx** out) {
+    if (!out) return fail(ACS_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int n = acs_device_count();
+    if (n <= 0) return fail(ACS_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(ACS_ERR_INVALID, "device index out of range");
+    ACS_CUDA(cudaSetDevice(device));
+    acs_ctx* c = new acs_ctx();
+    c->device = device;
+    for (int k = 0; k < kStreams; ++k) ACS_CUDA(cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking));
+    ACS_CUDA(cudaMalloc(&c->d_err, 2 * sizeof(unsigned long long)));
+    ACS_CUDA(cudaMallocHost(&c->h_err, 2 * sizeof(unsigned long long)));
+    *out = c;
+    return ACS_OK;
+}
+
+void acs_ctx_destroy(acs_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int k = 0; k < kStreams; ++k) {
+        if (c->streams[k]) {
+            cudaStreamSynchronize(c->streams[k]);
+            cudaStreamDestroy(c->streams[k]);
+        }
+        c->scratch[k].release();
+    }
+    if (c->d_err) cudaFree(c->d_err);
+    if (c->h_err) cudaFreeHost(c->h_err);
+    delete c;
+}
+
+// ---------------------------------------------------------------- device-pointer API
+int acs_moves_batch(const int8_t* d_in, const uint8_t* d_action, int8_t* d_out, uint8_t* d_lens,
+                    uint8_t* d_status, uint64_t* d_err, int64_t n, int mrl, int cyclical, void* stream) {
+    if (n < 0 || (n > 0 && (!d_in || !d_action || !d_out))) return fail(ACS_ERR_INVALID, "null buffer");
+    if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
+    acs::StepParams P{};
+    P.in = d_in;
+    P.out = d_out;
+    P.action = d_action;
+    P.lens = d_lens;
+    P.status = d_status;
+    P.err = reinterpret_cast<unsigned long long*>(d_err);
+    P.n = n;
+    P.mrl = mrl;
+    P.cyclical = cyclical ? 1 : 0;
+    P.bulk_ok = aligned16(d_in) && aligned16(d_out);
+    ACS_CUDA(acs::launch_step(P, static_cast<cudaStream_t>(stream)));
+    return ACS_OK;
+}
+
+int acs_env_step_batch(int8_t* d_state, const uint8_t* d_action, int32_t* d_reward, uint8_t* d_done,
+                       uint8_t* d_truncated, int32_t* d_step_count, uint8_t* d_lens, uint8_t* d_status,
+                       uint64_t* d_err, int64_t n, int mrl, int horizon, void* stream) {
+    if (n < 0 || (n > 0 && (!d_state || !d_action || !d_reward || !d_done || !d_truncated || !d_step_count)))
+        return fail(ACS_ERR_INVALID, "null buffer");
+    if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
+    acs::StepParams P{};
+    P.in = d_state;
+    P.out = d_state;
+    P.action = d_action;
+    P.lens = d_lens;
+    P.status = d_status;
+    P.err = reinterpret_cast<unsigned long long*>(d_err);
+    P.reward = d_reward;
+    P.done = d_done;
+    P.truncated = d_truncated;
+    P.step_count = d_step_count;
+    P.n = n;
+    P.mrl = mrl;
+    P.cyclical = 1;  // ac_env.py:97-99 uses ACMove's default cyclical=True
+    P.horizon = horizon;
+    P.max_reward = horizon * mrl * 2;  // ac_env.py:80
+    P.bulk_ok = aligned16(d_state);
+    ACS_CUDA(acs::launch_step(P, static_cast<cudaStream_t>(stream)));
+    return ACS_OK;
+}
+
+int acs_validate_batch(const int8_t* d_in, uint8_t* d_flags, int64_t n, int mrl, void* stream) {
+    if (n < 0 || (n > 0 && (!d_in || !d_flags)) || mrl < 1) return fail(ACS_ERR_INVALID, "bad argument");
+    ACS_CUDA(acs::launch_validate(d_in, d_flags, n, mrl, static_cast<cudaStream_t>(stream)));
+    return ACS_OK;
+}
+
+int acs_generic_batch(int op, const int8_t* d_in, const uint8_t* d_action, int8_t* d_out, int32_t* d_aux,
+                      uint8_t* d_status, int64_t n, int width, int i, int j, int sign, int cyclical,
+                      void* stream) {
+    if (n < 0 || (n > 0 && (!d_in || !d_out || !d_aux))) return fail(ACS_ERR_INVALID, "null buffer");
+    if (op < 0 || op > 4) return fail(ACS_ERR_INVALID, "unknown op");
+    if (op == ACS_OP_ACMOVE && n > 0 && !d_action) return fail(ACS_ERR_INVALID, "ACMOVE needs actions");
+    if (width < 1 || width > 254 || (op != ACS_OP_SIMPLIFY_RELATOR && (width & 1)))
+        return fail(ACS_ERR_UNSUPPORTED, "generic kernels need 1 <= width <= 254 (even for presentations)");
+    acs::GenericParams G{};
+    G.op = op;
+    G.in = d_in;
+    G.action = d_action;
+    G.out = d_out;
+    G.aux = d_aux;
+    G.status = d_status;
+    G.n = n;
+    G.width = width;
+    G.i = i;
+    G.j = j;
+    G.sign = sign;
+    G.cyclical = cyclical ? 1 : 0;
+    ACS_CUDA(acs::launch_generic(G, static_cast<cudaStream_t>(stream)));
+    return ACS_OK;
+}
+
+// ---------------------------------------------------------------- host-pointer API
+int acs_moves_batch_host(acs_ctx* c, const int8_t* h_in, const uint8_t* h_action, int8_t* h_out, uint8_t* h_lens,
+                         uint8_t* h_status, int64_t n, int mrl, int cyclical) {
+    if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    if (n < 0 || (n > 0 && (!h_in || !h_action || !h_out))) return fail(ACS_ERR_INVALID, "null buffer");
+    if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
+    ACS_CUDA(cudaSetDevice(c->device));
+    const size_t rowb = 2 * (size_t)mrl;
+    const int64_t chunk = n < kChunkRows ? (n > 0 ? n : 1) : kChunkRows;
+    // per-stream scratch: state (in place) | action | lens | status, each 256-byte aligned
+    const size_t o_act = align_up((size_t)chunk * rowb, 256);
+    const size_t o_len = o_act + align_up((size_t)chunk, 256);
+    const size_t o_st = o_len + align_up((size_t)chunk * 2, 256);
+    const size_t total = o_st + align_up((size_t)chunk, 256);
+    int64_t ci = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk, ++ci) {
+        const int k = (int)(ci % kStreams);
+        const int64_t m = (n - r0) < chunk ? (n - r0) : chunk;
+        int rc = c->scratch[k].reserve(total);
+        if (rc != ACS_OK) return rc;
+        uint8_t* base = static_cast<uint8_t*>(c->scratch[k].p);
+        cudaStream_t s = c->streams[k];
+        ACS_CUDA(cudaMemcpyAsync(base, h_in + r0 * rowb, (size_t)m * rowb, cudaMemcpyHostToDevice, s));
+        ACS_CUDA(cudaMemcpyAsync(base + o_act, h_action + r0, (size_t)m, cudaMemcpyHostToDevice, s));
+        rc = acs_moves_batch(reinterpret_cast<int8_t*>(base), base + o_act, reinterpret_cast<int8_t*>(base),
+                             h_lens ? base + o_len : nullptr, h_status ? base + o_st : nullptr, nullptr, m, mrl,
+                             cyclical, s);
+        if (rc != ACS_OK) return rc;
+        ACS_CUDA(cudaMemcpyAsync(h_out + r0 * rowb, base, (size_t)m * rowb, cudaMemcpyDeviceToHost, s));
+        if (h_lens) ACS_CUDA(cudaMemcpyAsync(h_lens + 2 * r0, base + o_len, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
+        if (h_status) ACS_CUDA(cudaMemcpyAsync(h_status + r0, base + o_st, (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < kStreams; ++k) ACS_CUDA(cudaStreamSynchronize(c->streams[k]));
+    return ACS_OK;
+}
+
+int acs_env_step_host(acs_ctx* c, int8_t* d_state, int32_t* d_step_count, const uint8_t* h_action, int8_t* h_obs,
+                      int32_t* h_reward, uint8_t* h_done, uint8_t* h_truncated, int64_t n, int mrl, int horizon,
+                      int64_t* n_bad) {
+    if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    if (n < 0 || (n > 0 && (!d_state || !d_step_count || !h_action || !h_reward || !h_done || !h_truncated)))
+        return fail(ACS_ERR_INVALID, "null buffer");
+    if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
+    ACS_CUDA(cudaSetDevice(c->device));
+    const size_t rowb = 2 * (size_t)mrl;
+    // chunk rows: keep tile (128-row) granularity so device-side tiles stay 16-byte aligned
+    const int64_t chunk = n < kChunkRows ? (n > 0 ? n : 1) : kChunkRows;
+    const size_t o_rew = align_up((size_t)chunk, 256);
+    const size_t o_done = o_rew + align_up((size_t)chunk * 4, 256);
+    const size_t o_tr = o_done + align_up((size_t)chunk, 256);
+    const size_t total = o_tr + align_up((size_t)chunk, 256);
+    c->h_err[0] = 0;
+    c->h_err[1] = ~0ull;
+    ACS_CUDA(cudaMemcpyAsync(c->d_err, c->h_err, 16, cudaMemcpyHostToDevice, c->streams[0]));
+    ACS_CUDA(cudaStreamSynchronize(c->streams[0]));
+    int64_t ci = 0;
+    for (int64_t r0 = 0; r0 < n; r0 += chunk, ++ci) {
+        const int k = (int)(ci % kStreams);
+        const int64_t m = (n - r0) < chunk ? (n - r0) : chunk;
+        int rc = c->scratch[k].reserve(total);
+        if (rc != ACS_OK) return rc;
+        uint8_t* base = static_cast<uint8_t*>(c->scratch[k].p);
+        cudaStream_t s = c->streams[k];
+        ACS_CUDA(cudaMemcpyAsync(base, h_action + r0, (size_t)m, cudaMemcpyHostToDevice, s));
+        rc = acs_env_step_batch(d_state + r0 * rowb, base, reinterpret_cast<int32_t*>(base + o_rew), base + o_done,
+                                base + o_tr, d_step_count + r0, nullptr, nullptr,
+                                reinterpret_cast<uint64_t*>(c->d_err), m, mrl, horizon, s);
+        if (rc != ACS_OK) return rc;
+        if (h_obs) ACS_CUDA(cudaMemcpyAsync(h_obs + r0 * rowb, d_state + r0 * rowb, (size_t)m * rowb, cudaMemcpyDeviceToHost, s));
+        ACS_CUDA(cudaMemcpyAsync(h_reward + r0, base + o_rew, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        ACS_CUDA(cudaMemcpyAsync(h_done + r0, base + o_done, (size_t)m, cudaMemcpyDeviceToHost, s));
+        ACS_CUDA(cudaMemcpyAsync(h_truncated + r0, base + o_tr, (size_t)m, cudaMemcpyDeviceToHost, s));
+    }
+    for (int k = 0; k < kStreams; ++k) ACS_CUDA(cudaStreamSynchronize(c->streams[k]));
+    ACS_CUDA(cudaMemcpy(c->h_err, c->d_err, 16, cudaMemcpyDeviceToHost));
+    if (n_bad) *n_bad = (int64_t)c->h_err[0];
+    return ACS_OK;
+}
+
+int acs_validate_batch_host(acs_ctx* c, const int8_t* h_in, uint8_t* h_flags, int64_t n, int mrl) {
+    if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    if (n < 0 || (n > 0 && (!h_in || !h_flags)) || mrl < 1) return fail(ACS_ERR_INVALID, "bad argument");
+    if (n == 0) return ACS_OK;
+    ACS_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * 2 * mrl;
+    const size_t o_f = align_up(bytes, 256);
+    int rc = c->scratch[0].reserve(o_f + (size_t)n);
+    if (rc != ACS_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(c->scratch[0].p);
+    cudaStream_t s = c->streams[0];
+    ACS_CUDA(cudaMemcpyAsync(base, h_in, bytes, cudaMemcpyHostToDevice, s));
+    rc = acs_validate_batch(reinterpret_cast<int8_t*>(base), base + o_f, n, mrl, s);
+    if (rc != ACS_OK) return rc;
+    ACS_CUDA(cudaMemcpyAsync(h_flags, base + o_f, (size_t)n, cudaMemcpyDeviceToHost, s));
+    ACS_CUDA(cudaStreamSynchronize(s));
+    return ACS_OK;
+}
+
+int acs_generic_host(acs_ctx* c, int op, const int8_t* h_in, const uint8_t* h_action, int8_t* h_out, int32_t* h_aux,
+                     uint8_t* h_status, int64_t n, int width, int i, int j, int sign, int cyclical) {
+    if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    if (n < 0 || (n > 0 && (!h_in || !h_out || !h_aux || !h_status))) return fail(ACS_ERR_INVALID, "null buffer");
+    if (n == 0) return ACS_OK;
+    ACS_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)n * width;
+    const int aux_per_row = (op == ACS_OP_ACMOVE || op == ACS_OP_SIMPLIFY_PRESENTATION) ? 2 : 1;
+    const size_t o_out = align_up(bytes, 256);
+    const size_t o_act = o_out + align_up(bytes, 256);
+    const size_t o_aux = o_act + align_up((size_t)n, 256);
+    const size_t o_st = o_aux + align_up((size_t)n * 4 * aux_per_row, 256);
+    int rc = c->scratch[0].reserve(o_st + (size_t)n);
+    if (rc != ACS_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(c->scratch[0].p);
+    cudaStream_t s = c->streams[0];
+    ACS_CUDA(cudaMemcpyAsync(base, h_in, bytes, cudaMemcpyHostToDevice, s));
+    if (h_action) ACS_CUDA(cudaMemcpyAsync(base + o_act, h_action, (size_t)n, cudaMemcpyHostToDevice, s));
+    ACS_CUDA(cudaMemsetAsync(base + o_aux, 0, (size_t)n * 4 * aux_per_row, s));
+    rc = acs_generic_batch(op, reinterpret_cast<int8_t*>(base), h_action ? base + o_act : nullptr,
+                           reinterpret_cast<int8_t*>(base + o_out), reinterpret_cast<int32_t*>(base + o_aux),
+                           base + o_st, n, width, i, j, sign, cyclical, s);
+    if (rc != ACS_OK) return rc;
+    ACS_CUDA(cudaMemcpyAsync(h_out, base + o_out, bytes, cudaMemcpyDeviceToHost, s));
+    ACS_CUDA(cudaMemcpyAsync(h_aux, base + o_aux, (size_t)n * 4 * aux_per_row, cudaMemcpyDeviceToHost, s));
+    ACS_CUDA(cudaMemcpyAsync(h_status, base + o_st, (size_t)n, cudaMemcpyDeviceToHost, s));
+    ACS_CUDA(cudaStreamSynchronize(s));
+    return ACS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+/*
+ * acsolver_b200.h -- C ABI of libacsolver_b200.so, the B200 (sm_100a) implementation of
+ * AC-Solver's AC-move transition function and of the BFS / greedy searches built on it.
+ *
+ * The reference (shehper/AC-Solver) has no FFI: its seam is a Python function API on
+ * host numpy arrays.  Every entry point below names the reference function it replaces
+ * (paths relative to the reference root).  Two flavours exist for the batched ops:
+ *   *_host : plain HOST pointers in and out -- what a reference-side binding (ctypes,
+ *            see INTEGRATION.md) calls; host<->device copies happen inside the call,
+ *            pipelined in chunks over several CUDA streams;
+ *   no suffix : DEVICE pointers + a cudaStream_t (as void*) for GPU-resident callers
+ *            (PPO rollouts with the policy in torch); asynchronous, nothing is copied.
+ *
+ * Conventions
+ *   - A presentation is 2*mrl int8 letters: relator 0 then relator 1, letters in
+ *     {+1,-1,+2,-2} = {x, x^-1, y, y^-1}, zero-padded on the right (envs/utils.py:4-7).
+ *     Rows of a batch are contiguous with stride 2*mrl bytes.  1 <= mrl <= 64 for the
+ *     packed kernels, <= 127 for the generic byte kernels.
+ *   - Every function returns ACS_OK (0) or a negative ACS_ERR_* code; nothing throws
+ *     across the ABI.  acs_last_error() returns a thread-local message.
+ *   - Per-row `status` bytes report what the reference would have raised for that row:
+ *     ACS_ROW_OK, ACS_ROW_ASSERT (AssertionError, envs/utils.py:261-263) or
+ *     ACS_ROW_INDEX (IndexError, envs/ac_moves.py:119).  Such rows are left unchanged.
+ *   - The caller owns every buffer it passes.  The library owns only what *_create
+ *     returns.  No global mutable state; a context may be used by one thread at a time.
+ *   - The batched packed kernels require rows that are zero right-padded over the
+ *     alphabet {+-1,+-2} (check once with acs_validate_batch); words need not be reduced
+ *     and relators may be empty.  The generic kernels accept any int8 letters.
+ */
+#ifndef ACSOLVER_B200_H
+#define ACSOLVER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACS_OK 0
+#define ACS_ERR_INVALID (-1)     /* bad argument                                   */
+#define ACS_ERR_CUDA (-2)        /* CUDA runtime error, see acs_last_error()       */
+#define ACS_ERR_UNSUPPORTED (-3) /* e.g. mrl out of range for the packed kernels   */
+#define ACS_ERR_NOMEM (-4)       /* device or host allocation failed               */
+#define ACS_ERR_NO_DEVICE (-5)   /* no CUDA device: there is NO CPU fallback       */
+
+#define ACS_ROW_OK 0
+#define ACS_ROW_ASSERT 1
+#define ACS_ROW_INDEX 2
+
+/* generic ops (acs_generic_*): which reference function is evaluated */
+#define ACS_OP_ACMOVE 0                /* envs/ac_moves.py:159-231 ACMove               */
+#define ACS_OP_CONCAT_RAW 1            /* envs/ac_moves.py:4-76   concatenate_relators  */
+#define ACS_OP_CONJ_RAW 2              /* envs/ac_moves.py:79-156 conjugate             */
+#define ACS_OP_SIMPLIFY_RELATOR 3      /* envs/utils.py:175-240   simplify_relator      */
+#define ACS_OP_SIMPLIFY_PRESENTATION 4 /* envs/utils.py:243-280   simplify_presentation */
+
+typedef struct acs_ctx acs_ctx;
+
+int acs_version(void);
+const char *acs_last_error(void);
+/* number of visible CUDA devices (0 if none / driver missing) */
+int acs_device_count(void);
+
+/* A context binds a device and owns the streams / scratch used by the *_host calls. */
+int acs_ctx_create(int device, acs_ctx **out);
+void acs_ctx_destroy(acs_ctx *ctx);
+
+/* ---- ACMove, batched (envs/ac_moves.py:159-231) --------------------------------- */
+/* out may alias in.  lens [n,2] (recomputed lengths), status [n], err (two uint64:
+ * number of non-OK rows, smallest such row; must be initialised to {0, ~0}) may be NULL. */
+int acs_moves_batch(const int8_t *d_in, const uint8_t *d_action, int8_t *d_out, uint8_t *d_lens,
+                    uint8_t *d_status, uint64_t *d_err, int64_t n, int mrl, int cyclical, void *stream);
+int acs_moves_batch_host(acs_ctx *ctx, const int8_t *h_in, const uint8_t *h_action, int8_t *h_out,
+                         uint8_t *h_lens, uint8_t *h_status, int64_t n, int mrl, int cyclical);
+
+/* ---- ACEnv.step, batched (envs/ac_env.py:95-113) --------------------------------- */
+/* n independent environments; state [n,2*mrl] updated in place (cyclical=True as in the
+ * reference); reward = horizon*mrl*2 if done else -(len0+len1); step_count += 1;
+ * truncated = step_count >= horizon.  d_lens / d_status / d_err may be NULL. */
+int acs_env_step_batch(int8_t *d_state, const uint8_t *d_action, int32_t *d_reward, uint8_t *d_done,
+                       uint8_t *d_truncated, int32_t *d_step_count, uint8_t *d_lens, uint8_t *d_status,
+                       uint64_t *d_err, int64_t n, int mrl, int horizon, void *stream);
+/* Same step with the environment state RESIDENT on the device (d_state, d_step_count
+ * owned by the caller) and host actions in / host observations, rewards and flags out:
+ * the vector-env call of agents/training.py:154-156.  h_obs may be NULL (observations
+ * stay on the device).  *n_bad receives the number of rows whose move raised. */
+int acs_env_step_host(acs_ctx *ctx, int8_t *d_state, int32_t *d_step_count, const uint8_t *h_action,
+                      int8_t *h_obs, int32_t *h_reward, uint8_t *h_done, uint8_t *h_truncated,
+                      int64_t n, int mrl, int horizon, int64_t *n_bad);
+
+/* ---- boundary validation (envs/utils.py:13-54) ------------------------------------ */
+/* flags[row]: bit0 is_array_valid_presentation, bit1 letters in {0,+-1,+-2},
+ * bit2 zeros only on the right of each half. */
+int acs_validate_batch(const int8_t *d_in, uint8_t *d_flags, int64_t n, int mrl, void *stream);
+int acs_validate_batch_host(acs_ctx *ctx, const int8_t *h_in, uint8_t *h_flags, int64_t n, int mrl);
+
+/* ---- generic byte-domain ops, any int8 alphabet ----------------------------------- */
+/* width = letters per row (2*mrl; the relator width for SIMPLIFY_RELATOR).
+ * aux: ACMOVE / SIMPLIFY_PRESENTATION -> int32 [n,2] lengths; *_RAW -> int32 [n] new
+ * length of r_i, -1 rejected (row unchanged), -2 IndexError; SIMPLIFY_RELATOR -> [n]. */
+int acs_generic_batch(int op, const int8_t *d_in, const uint8_t *d_action, int8_t *d_out, int32_t *d_aux,
+                      uint8_t *d_status, int64_t n, int width, int i, int j, int sign, int cyclical,
+                      void *stream);
+int acs_generic_host(acs_ctx *ctx, int op, const int8_t *h_in, const uint8_t *h_action, int8_t *h_out,
+                     int32_t *h_aux, uint8_t *h_status, int64_t n, int width, int i, int j, int sign,
+                     int cyclical);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
