@@ -25,6 +25,9 @@ struct StepParams {
     int bulk_ok;            // in/out are 16-byte aligned: TMA bulk copies allowed
 };
 
+// thread-local error text behind acs_last_error() (capi.cu)
+void set_last_error(const char* msg);
+
 cudaError_t launch_step(const StepParams& P, cudaStream_t s);
 
 // byte-domain reference-semantics kernel for any int8 alphabet (generic_kernel.cu)

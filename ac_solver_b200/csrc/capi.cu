@@ -57,6 +57,10 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace
 
+namespace acs {
+void set_last_error(const char* msg) { g_err = msg ? msg : ""; }
+}  // namespace acs
+
 struct acs_ctx {
     int device = 0;
     cudaStream_t streams[kStreams] = {};

@@ -105,6 +105,33 @@ int acs_generic_host(acs_ctx *ctx, int op, const int8_t *h_in, const uint8_t *h_
                      int32_t *h_aux, uint8_t *h_status, int64_t n, int width, int i, int j, int sign,
                      int cyclical);
 
+/* ---- searches (search/breadth_first.py:15-97, search/greedy.py:15-121) ------------ */
+typedef struct {
+    int32_t solved;        /* a child of total length 2 was generated                   */
+    int32_t status;        /* ACS_ROW_* of the move that raised in reference order, or 0 */
+    int32_t budget_hit;    /* the reference would print "Exiting search as ..."          */
+    int32_t path_len;      /* (action,length) pairs written to path                      */
+    int64_t n_visited;     /* len(tree_nodes) at return                                  */
+    int64_t n_expanded;    /* nodes whose 12 children were generated                     */
+    int64_t n_moves;       /* ACMove evaluations the reference would have made           */
+    int64_t frontier_left; /* len(to_explore) at return                                  */
+    int32_t n_levels;      /* BFS levels / greedy rounds executed on the device          */
+    int32_t n_minlen;      /* entries of minlen_log                                      */
+    int32_t minlen_log[128]; /* successive "New minimal length found" values (verbose)   */
+    double seconds_device; /* CUDA-event time of the search proper                       */
+} acs_search_result;
+
+typedef struct acs_bfs acs_bfs;
+/* max_nodes: node budget; device capacity is derived from it (16 B/node keys for mrl <= 29,
+ * 32 B for mrl <= 61, + 8 B parent link + 16 B of hash table).  ctx may be NULL. */
+int acs_bfs_create(acs_ctx *ctx, int device, int mrl, int64_t max_nodes, int cyclical, acs_bfs **out);
+/* Runs the whole search on the device.  path: int32 pairs, capacity path_cap pairs. */
+int acs_bfs_run(acs_bfs *b, const int8_t *h_presentation, int32_t *h_path, int path_cap,
+                acs_search_result *res);
+/* visited states in insertion (FIFO) order as int8 rows; returns rows written via *n_out */
+int acs_bfs_visited(acs_bfs *b, int8_t *h_out, int64_t cap_rows, int64_t *n_out);
+void acs_bfs_destroy(acs_bfs *b);
+
 #ifdef __cplusplus
 }
 #endif
