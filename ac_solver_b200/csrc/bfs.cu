@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_expand_kernel(const BfsArgs A
             const uint64_t fp = h >> 40;
             const uint64_t mine = (fp << 40) | (A.n_nodes + c + 1);
             uint64_t s = h & A.tmask;
+            uint64_t probes = 0;
             for (;;) {
                 uint64_t cur = __ldcg(&A.table[s]);  // L2 read: other SMs update slots atomically
                 if (cur == 0) {
@@ -211,6 +212,10 @@ __global__ void __launch_bounds__(kBfsThreads) bfs_expand_kernel(const BfsArgs A
                     }
                 }
                 s = (s + 1) & A.tmask;
+                if (++probes > A.tmask) {  // table full: cannot happen with the host's chunk sizing
+                    atomicMin(&A.ctrl->err, (gid << 2) | 3u);
+                    break;
+                }
             }
         }
     }
@@ -554,7 +559,11 @@ int bfs_run_impl(acs_bfs* b, const int8_t* h_presentation, int32_t* h_path, int 
             level_end = n_nodes;
             ++levels;
         }
-        const uint64_t F = std::min<uint64_t>(std::min<uint64_t>(level_end - head, b->chunk_cap), n_nodes - head);
+        // A chunk plants up to 12*F tentative entries beside the n_nodes committed ones: keep
+        // the table at most 3/4 full (tcap >= 2*cap, so at least cap/24 parents always fit).
+        const uint64_t room = (3 * (b->tcap / 4) > n_nodes) ? (3 * (b->tcap / 4) - n_nodes) / 12 : 0;
+        const uint64_t F = std::min<uint64_t>(std::min<uint64_t>(level_end - head, b->chunk_cap),
+                                              std::max<uint64_t>(room, 1));
         const unsigned nblocks = (unsigned)((F + kParentsPerBlock - 1) / kParentsPerBlock);
         // reset the control block
         for (auto& v : b->h_ctrl->first_len) v = kNone;
@@ -596,6 +605,10 @@ int bfs_run_impl(acs_bfs* b, const int8_t* h_presentation, int32_t* h_path, int 
                 sol_here = true;
                 cut = false;
             }
+        }
+        if (b->h_ctrl->err != kNone && (b->h_ctrl->err & 3) == 3) {
+            g_bfs_err = "bfs: internal error, visited table overflow";
+            return ACS_ERR_CUDA;
         }
         if (b->h_ctrl->err != kNone) {
             const uint64_t ec = (b->h_ctrl->err >> 2) - head * 12;
