@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libacsolver_b200.so")
 ACS_OK = 0
 ROW_OK, ROW_ASSERT, ROW_INDEX = 0, 1, 2
 OP_ACMOVE, OP_CONCAT_RAW, OP_CONJ_RAW, OP_SIMPLIFY_RELATOR, OP_SIMPLIFY_PRESENTATION = range(5)
+FLAG_CYCLICAL, FLAG_NORMALIZED = 1, 2
 
 
 class AcsError(RuntimeError):
@@ -50,8 +51,8 @@ _SIGS = {
     "acs_ctx_destroy": (None, [_P]),
     "acs_moves_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
     "acs_moves_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int]),
-    "acs_env_step_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P]),
-    "acs_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int,
+    "acs_env_step_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
+    "acs_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int64)]),
     "acs_validate_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "acs_validate_batch_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),

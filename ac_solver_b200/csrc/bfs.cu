@@ -71,28 +71,30 @@ __host__ __device__ __forceinline__ uint64_t key_hash(const Key<W>& a) {
     return mix64(h);
 }
 template <int W>
-__device__ __forceinline__ Key<W> make_key(const Rel<W>& r0, const Rel<W>& r1) {
+__device__ __forceinline__ Key<W> make_key(const Rel<2 * W>& r0, const Rel<2 * W>& r1) {
     Key<W> q;
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        q.k[i] = r0.b.w[i];
-        q.k[W + i] = r1.b.w[i];
+        q.k[i] = (uint64_t)r0.b.w[2 * i] | ((uint64_t)r0.b.w[2 * i + 1] << 32);
+        q.k[W + i] = (uint64_t)r1.b.w[2 * i] | ((uint64_t)r1.b.w[2 * i + 1] << 32);
     }
     q.k[W - 1] |= (uint64_t)r0.len << 58;
     q.k[2 * W - 1] |= (uint64_t)r1.len << 58;
     return q;
 }
 template <int W>
-__device__ __forceinline__ void split_key(const Key<W>& q, Rel<W>& r0, Rel<W>& r1) {
+__device__ __forceinline__ void split_key(const Key<W>& q, Rel<2 * W>& r0, Rel<2 * W>& r1) {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
-        r0.b.w[i] = q.k[i];
-        r1.b.w[i] = q.k[W + i];
+        r0.b.w[2 * i] = (uint32_t)q.k[i];
+        r0.b.w[2 * i + 1] = (uint32_t)(q.k[i] >> 32);
+        r1.b.w[2 * i] = (uint32_t)q.k[W + i];
+        r1.b.w[2 * i + 1] = (uint32_t)(q.k[W + i] >> 32);
     }
     r0.len = (int)(q.k[W - 1] >> 58);
     r1.len = (int)(q.k[2 * W - 1] >> 58);
-    r0.b.w[W - 1] &= (1ull << 58) - 1;
-    r1.b.w[W - 1] &= (1ull << 58) - 1;
+    r0.b.w[2 * W - 1] &= (1u << 26) - 1;
+    r1.b.w[2 * W - 1] &= (1u << 26) - 1;
 }
 template <int W>
 __device__ __forceinline__ Key<W> load_key(const uint64_t* keys, uint64_t idx) {
@@ -146,16 +148,20 @@ struct BfsArgs {
     int mrl;
     int cyclical;
     int min_len;       // smallest total length seen before this chunk
+    int trusted;       // all parents of the chunk are normal forms (every chunk but the root's)
 };
 
 template <int W>
 __device__ __forceinline__ int child_of(const BfsArgs& A, uint64_t parent, int action, Key<W>& child, Key<W>& pk,
                                         int& total_len) {
     pk = load_key<W>(A.keys, parent);
-    Rel<W> r0, r1;
+    Rel<2 * W> r0, r1;
     split_key<W>(pk, r0, r1);
     bool co;
-    const int st = apply_move<W>(r0, r1, action, A.mrl, A.cyclical != 0, co);
+    // every node after the root was produced by apply_move with this cyclical flag, so it is
+    // a normal form; only the caller-supplied root needs the reference's full simplification
+    const int st = A.trusted ? apply_move<2 * W, true>(r0, r1, action, A.mrl, A.cyclical != 0, co)
+                             : apply_move<2 * W, false>(r0, r1, action, A.mrl, A.cyclical != 0, co);
     child = make_key<W>(r0, r1);
     total_len = r0.len + r1.len;
     return st;
@@ -348,10 +354,10 @@ template <int W>
 __global__ void bfs_unpack_kernel(const uint64_t* keys, int8_t* out, uint64_t n, int mrl) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Rel<W> r0, r1;
+    Rel<2 * W> r0, r1;
     split_key<W>(load_key<W>(keys, i), r0, r1);
-    unpack_bytes<W>(out + i * 2 * mrl, r0, mrl);
-    unpack_bytes<W>(out + i * 2 * mrl + mrl, r1, mrl);
+    unpack_bytes<2 * W>(out + i * 2 * mrl, r0, mrl);
+    unpack_bytes<2 * W>(out + i * 2 * mrl + mrl, r1, mrl);
 }
 
 }  // namespace acs
@@ -577,6 +583,7 @@ int bfs_run_impl(acs_bfs* b, const int8_t* h_presentation, int32_t* h_path, int 
         A.nparents = F;
         A.n_nodes = n_nodes;
         A.min_len = min_len;
+        A.trusted = head > 0 ? 1 : 0;
         A.limit = F * 12;
         bfs_expand_kernel<W><<<nblocks, kBfsThreads, 0, s>>>(A);
         bfs_mark_kernel<<<nblocks, kBfsThreads, 0, s>>>(A);

@@ -116,7 +116,7 @@ void acs_ctx_destroy(acs_ctx* c) {
 
 // ---------------------------------------------------------------- device-pointer API
 int acs_moves_batch(const int8_t* d_in, const uint8_t* d_action, int8_t* d_out, uint8_t* d_lens,
-                    uint8_t* d_status, uint64_t* d_err, int64_t n, int mrl, int cyclical, void* stream) {
+                    uint8_t* d_status, uint64_t* d_err, int64_t n, int mrl, int flags, void* stream) {
     if (n < 0 || (n > 0 && (!d_in || !d_action || !d_out))) return fail(ACS_ERR_INVALID, "null buffer");
     if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
     acs::StepParams P{};
@@ -128,7 +128,8 @@ int acs_moves_batch(const int8_t* d_in, const uint8_t* d_action, int8_t* d_out, 
     P.err = reinterpret_cast<unsigned long long*>(d_err);
     P.n = n;
     P.mrl = mrl;
-    P.cyclical = cyclical ? 1 : 0;
+    P.cyclical = (flags & ACS_FLAG_CYCLICAL) ? 1 : 0;
+    P.trusted = (flags & ACS_FLAG_NORMALIZED) ? 1 : 0;
     P.bulk_ok = aligned16(d_in) && aligned16(d_out);
     ACS_CUDA(acs::launch_step(P, static_cast<cudaStream_t>(stream)));
     return ACS_OK;
@@ -136,7 +137,7 @@ int acs_moves_batch(const int8_t* d_in, const uint8_t* d_action, int8_t* d_out, 
 
 int acs_env_step_batch(int8_t* d_state, const uint8_t* d_action, int32_t* d_reward, uint8_t* d_done,
                        uint8_t* d_truncated, int32_t* d_step_count, uint8_t* d_lens, uint8_t* d_status,
-                       uint64_t* d_err, int64_t n, int mrl, int horizon, void* stream) {
+                       uint64_t* d_err, int64_t n, int mrl, int horizon, int flags, void* stream) {
     if (n < 0 || (n > 0 && (!d_state || !d_action || !d_reward || !d_done || !d_truncated || !d_step_count)))
         return fail(ACS_ERR_INVALID, "null buffer");
     if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
@@ -154,6 +155,7 @@ int acs_env_step_batch(int8_t* d_state, const uint8_t* d_action, int32_t* d_rewa
     P.n = n;
     P.mrl = mrl;
     P.cyclical = 1;  // ac_env.py:97-99 uses ACMove's default cyclical=True
+    P.trusted = (flags & ACS_FLAG_NORMALIZED) ? 1 : 0;
     P.horizon = horizon;
     P.max_reward = horizon * mrl * 2;  // ac_env.py:80
     P.bulk_ok = aligned16(d_state);
@@ -194,7 +196,7 @@ int acs_generic_batch(int op, const int8_t* d_in, const uint8_t* d_action, int8_
 
 // ---------------------------------------------------------------- host-pointer API
 int acs_moves_batch_host(acs_ctx* c, const int8_t* h_in, const uint8_t* h_action, int8_t* h_out, uint8_t* h_lens,
-                         uint8_t* h_status, int64_t n, int mrl, int cyclical) {
+                         uint8_t* h_status, int64_t n, int mrl, int flags) {
     if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
     if (n < 0 || (n > 0 && (!h_in || !h_action || !h_out))) return fail(ACS_ERR_INVALID, "null buffer");
     if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
@@ -218,7 +220,7 @@ int acs_moves_batch_host(acs_ctx* c, const int8_t* h_in, const uint8_t* h_action
         ACS_CUDA(cudaMemcpyAsync(base + o_act, h_action + r0, (size_t)m, cudaMemcpyHostToDevice, s));
         rc = acs_moves_batch(reinterpret_cast<int8_t*>(base), base + o_act, reinterpret_cast<int8_t*>(base),
                              h_lens ? base + o_len : nullptr, h_status ? base + o_st : nullptr, nullptr, m, mrl,
-                             cyclical, s);
+                             flags, s);
         if (rc != ACS_OK) return rc;
         ACS_CUDA(cudaMemcpyAsync(h_out + r0 * rowb, base, (size_t)m * rowb, cudaMemcpyDeviceToHost, s));
         if (h_lens) ACS_CUDA(cudaMemcpyAsync(h_lens + 2 * r0, base + o_len, (size_t)m * 2, cudaMemcpyDeviceToHost, s));
@@ -230,7 +232,7 @@ int acs_moves_batch_host(acs_ctx* c, const int8_t* h_in, const uint8_t* h_action
 
 int acs_env_step_host(acs_ctx* c, int8_t* d_state, int32_t* d_step_count, const uint8_t* h_action, int8_t* h_obs,
                       int32_t* h_reward, uint8_t* h_done, uint8_t* h_truncated, int64_t n, int mrl, int horizon,
-                      int64_t* n_bad) {
+                      int flags, int64_t* n_bad) {
     if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
     if (n < 0 || (n > 0 && (!d_state || !d_step_count || !h_action || !h_reward || !h_done || !h_truncated)))
         return fail(ACS_ERR_INVALID, "null buffer");
@@ -258,7 +260,7 @@ int acs_env_step_host(acs_ctx* c, int8_t* d_state, int32_t* d_step_count, const 
         ACS_CUDA(cudaMemcpyAsync(base, h_action + r0, (size_t)m, cudaMemcpyHostToDevice, s));
         rc = acs_env_step_batch(d_state + r0 * rowb, base, reinterpret_cast<int32_t*>(base + o_rew), base + o_done,
                                 base + o_tr, d_step_count + r0, nullptr, nullptr,
-                                reinterpret_cast<uint64_t*>(c->d_err), m, mrl, horizon, s);
+                                reinterpret_cast<uint64_t*>(c->d_err), m, mrl, horizon, flags, s);
         if (rc != ACS_OK) return rc;
         if (h_obs) ACS_CUDA(cudaMemcpyAsync(h_obs + r0 * rowb, d_state + r0 * rowb, (size_t)m * rowb, cudaMemcpyDeviceToHost, s));
         ACS_CUDA(cudaMemcpyAsync(h_reward + r0, base + o_rew, (size_t)m * 4, cudaMemcpyDeviceToHost, s));

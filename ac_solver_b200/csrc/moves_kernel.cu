@@ -3,21 +3,21 @@
 // Reference semantics: ac_solver/envs/ac_moves.py:159-231 (ACMove) and
 // ac_solver/envs/ac_env.py:95-113 (ACEnv.step); paths relative to /root/reference.
 //
-// Design (HBM-bound integer rewriting, no tensor cores):
+// Design (integer rewriting, no tensor cores; the roofline is HBM, the practical limit is
+// the ALU pipe):
 //   * a tile of 128 rows (128 * 2*mrl bytes, 9216 B at mrl 36) is moved HBM -> shared
 //     memory by ONE TMA bulk copy (cp.async.bulk, mbarrier completion) and back by ONE
 //     bulk store, so global traffic is fully coalesced 16-byte bursts although a row is
 //     72 bytes (8-byte aligned only);
 //   * one thread owns one row: 64-bit conflict-free LDS of the row, int8 -> 2-bit codes
-//     with a multiply-gather, the move on registers (ac_core.cuh), 2-bit -> int8 with a
-//     PRMT table lookup, and only the REWRITTEN relator is stored back to the tile;
+//     with multiply-gathers (ac_pack.cuh), the move on registers (ac_core.cuh), 2-bit ->
+//     int8 with a PRMT table lookup, and only the REWRITTEN relator is stored back;
 //   * reward / done / truncated / step counter are fused into the same pass.
-// Budget at the measured 6.46 TB/s and 150 B per move: 26 warp-instructions per row per
-// SM; this thread-per-row, loop-free formulation needs about 12.
 #include <cstdint>
 #include <cuda_runtime.h>
 
 #include "ac_core.cuh"
+#include "ac_pack.cuh"
 #include "acs_internal.h"
 
 namespace acs {
@@ -66,58 +66,6 @@ __device__ __forceinline__ void tma_store_commit_and_wait_read() {
 }
 __device__ __forceinline__ void fence_async_proxy() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-// ---- int8 words <-> 2-bit codes -----------------------------------------------------
-// four letters (one 32-bit word) -> their four codes in the TOP byte of the result
-__device__ __forceinline__ uint32_t codes_top8(uint32_t w) {
-    uint32_t t = (w & 0x01010101u) | ((w >> 6) & 0x02020202u);
-    return t * 0x01041040u;  // 2^24 + 2^18 + 2^12 + 2^6: gathers the 2-bit fields, no carries
-}
-// top bytes of four products -> one 32-bit word of 16 codes
-__device__ __forceinline__ uint32_t gather4(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3) {
-    uint32_t a = __byte_perm(p0, p1, 0x0073);
-    uint32_t b = __byte_perm(p2, p3, 0x0073);
-    return __byte_perm(a, b, 0x5410);
-}
-
-template <int NW, int W>
-__device__ __forceinline__ Rel<W> pack_words(const uint32_t (&w)[NW]) {
-    Rel<W> r;
-    uint32_t nz = 0;
-    uint32_t piece[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int q = 0; q < (NW + 3) / 4; ++q) {
-        uint32_t p[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int j = 4 * q + k;
-            if (j < NW) {
-                p[k] = codes_top8(w[j]);
-                nz += (w[j] | (w[j] >> 1)) & 0x01010101u;
-            } else {
-                p[k] = 0;
-            }
-        }
-        piece[q] = gather4(p[0], p[1], p[2], p[3]);
-    }
-    r.b.w[0] = (uint64_t)piece[0] | ((uint64_t)piece[1] << 32);
-    if constexpr (W == 2) r.b.w[1] = (uint64_t)piece[2] | ((uint64_t)piece[3] << 32);
-    r.len = (int)((nz * 0x01010101u) >> 24);
-    return r;
-}
-
-// word j (letters 4j..4j+3) of a packed relator back to int8, zero beyond len
-template <int W>
-__device__ __forceinline__ uint32_t unpack_word(const Rel<W>& r, int j) {
-    uint32_t c8;
-    if (W == 1 || j < 8) c8 = (uint32_t)(r.b.w[0] >> (8 * j)) & 0xFFu;
-    else c8 = (uint32_t)(r.b.w[W - 1] >> (8 * (j - 8))) & 0xFFu;
-    uint32_t t = (c8 | (c8 << 4)) & 0x0F0Fu;
-    t = (t | (t << 2)) & 0x3333u;                       // one code per selector nibble
-    uint32_t bytes = __byte_perm(0xFFFE0102u, 0u, t);   // code -> letter table lookup
-    int n = max(8 * r.len - 32 * j, 0);
-    return bytes & __funnelshift_lc(0xFFFFFFFFu, 0u, n);  // low min(n,32) bits kept
 }
 
 // ---- per-row epilogue shared by both kernels ---------------------------------------
@@ -178,74 +126,167 @@ __device__ __forceinline__ void tile_store(const uint8_t* tile, const StepParams
     }
 }
 
+// store a packed relator as NW int8 words
+template <int NW, int N>
+__device__ __forceinline__ void store_relator(uint32_t* wp, const Rel<N>& t) {
+#pragma unroll
+    for (int i = 0; i < (NW + 1) / 2; ++i) {
+        uint32_t lo, hi;
+        unpack_pair<N>(t, i, lo, hi);
+        wp[2 * i] = lo;
+        if (2 * i + 1 < NW) wp[2 * i + 1] = hi;
+    }
+}
+
 // ---- fast kernel: mrl == 4*NW, rows read/written as whole words ----------------------
-template <int NW, int W>
+// Rows of a tile are partitioned by move class so that warps are uniform: threads
+// [0, n0) take the concatenation rows (ids 0..3, and invalid ids), the rest the
+// conjugation rows (ids 4..11), each class in row order (ballot + popc prefix).  With
+// TRUSTED states and cyclic reduction a conjugation is a rotation of the target relator by
+// one letter (or nothing), done directly on the int8 words with funnel shifts -- two thirds
+// of uniformly random moves never enter the packed domain.  Per-row results are staged in
+// shared memory and written back by the thread that owns the row index, so every global
+// access stays coalesced.
+template <int NW, bool TRUSTED>
 __global__ void __launch_bounds__(kTileRows, 8) ac_step_words_kernel(const StepParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ uint8_t s_perm[kTileRows];
+    __shared__ uint8_t s_act[kTileRows];
+    __shared__ uint32_t s_res[kTileRows];  // status << 16 | len0 << 8 | len1
+    __shared__ int s_wcnt[kTileRows / 32];
+    constexpr int N = (NW + 3) / 4;
     constexpr int ROWB = 8 * NW;  // bytes per row
+    const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * kTileRows;
     const int nrows = (int)min((int64_t)kTileRows, P.n - row0);
     const bool bulk = P.bulk_ok && nrows == kTileRows;
 
-    if (bulk && threadIdx.x == 0) {
+    if (bulk && tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     tile_load(smem, &bar, P, row0, nrows, bulk);
 
-    const int64_t row = row0 + threadIdx.x;
-    const bool active = threadIdx.x < nrows;
-    int action = 0;
-    if (active) action = P.action[row];  // overlaps the bulk copy
+    // ---- overlaps the bulk copy: per-row scalars and the class partition ----
+    const int64_t row = row0 + tid;
+    const bool active = tid < nrows;
+    int action = 255;
+    int sc = 0;
+    if (active) {
+        action = P.action[row];
+        if (P.reward) sc = P.step_count[row];
+    }
+    const bool is_concat = active && !(action >= 4 && action <= 11);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, is_concat);
+    const int lane = tid & 31, wid = tid >> 5;
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    s_act[tid] = (uint8_t)action;
+    __syncthreads();
+    int n0 = 0, before = __popc(bal & ((1u << lane) - 1u));
+#pragma unroll
+    for (int w = 0; w < kTileRows / 32; ++w) {
+        const int c = s_wcnt[w];
+        n0 += c;
+        if (w < wid) before += c;
+    }
+    s_perm[is_concat ? before : n0 + (tid - before)] = (uint8_t)tid;  // stable within each class
+    __syncthreads();
+    const int r = s_perm[tid];  // the row this thread processes
+    const int act = s_act[r];
 
     if (bulk) mbar_wait(&bar, 0);
-    else __syncthreads();
 
-    if (active) {
-        uint32_t w0[NW], w1[NW];
-        const uint2* rp = reinterpret_cast<const uint2*>(smem + (size_t)threadIdx.x * ROWB);
-        // 64-bit loads; relator 1 starts at word NW (a 64-bit boundary only when NW is even)
+    if (r < nrows) {
+        uint32_t* rw = reinterpret_cast<uint32_t*>(smem + (size_t)r * ROWB);
+        int status = ST_OK, len0, len1;
+        if (TRUSTED && P.cyclical && act >= 4 && act <= 11) {
+            // ---- conjugation of a normal form: rotation in the byte domain ----
+            const bool tgt1 = ((act + 1) & 1) != 0;
+            uint32_t u[NW], w[NW];
 #pragma unroll
-        for (int j = 0; j < NW; ++j) {
-            uint2 v = rp[j];
-            const int a = 2 * j, b = 2 * j + 1;
-            if (a < NW) w0[a] = v.x; else w1[a - NW] = v.x;
-            if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
-        }
-        Rel<W> r0 = pack_words<NW, W>(w0);
-        Rel<W> r1 = pack_words<NW, W>(w1);
-        RowOut o;
-        if (action > 11) {
-            o.status = ST_ASSERT;  // ac_moves.py:188-190
-            o.len0 = o.len1 = 0;
-        } else {
-            bool changed_other = false;
-            o.status = apply_move<W>(r0, r1, action, 4 * NW, P.cyclical != 0, changed_other);
-            o.len0 = r0.len;
-            o.len1 = r1.len;
-            if (o.status == ST_OK) {
-                const bool tgt1 = ((action + 1) & 1) != 0;
-                uint32_t* wp = reinterpret_cast<uint32_t*>(smem + (size_t)threadIdx.x * ROWB) + (tgt1 ? NW : 0);
-                const Rel<W>& t = tgt1 ? r1 : r0;
+            for (int j = 0; j < NW; ++j) {
+                u[j] = rw[(tgt1 ? NW : 0) + j];
+                w[j] = rw[(tgt1 ? 0 : NW) + j];
+            }
+            const int lu = count_letters<NW>(u), lw = count_letters<NW>(w);
+            len0 = tgt1 ? lw : lu;
+            len1 = tgt1 ? lu : lw;
+            if (lu == 0) status = ST_INDEX;       // relator_nonzero[0] on an empty array
+            else if (lw == 0) status = ST_ASSERT;  // utils.py:261-263
+            else {
+                uint8_t* ub = reinterpret_cast<uint8_t*>(rw + (tgt1 ? NW : 0));
+                int fix_pos;
+                uint32_t fix_val;
+                if (conj_rotate_words<NW>(u, lu, u[0] & 0xFFu, ub[lu - 1], conj_letter_byte(act), fix_pos, fix_val)) {
 #pragma unroll
-                for (int j = 0; j < NW; ++j) wp[j] = unpack_word<W>(t, j);
-                if (changed_other) {  // only for caller-supplied, not yet normalised rows
-                    uint32_t* op = reinterpret_cast<uint32_t*>(smem + (size_t)threadIdx.x * ROWB) + (tgt1 ? 0 : NW);
-                    const Rel<W>& q = tgt1 ? r0 : r1;
-#pragma unroll
-                    for (int j = 0; j < NW; ++j) op[j] = unpack_word<W>(q, j);
+                    for (int j = 0; j < NW; ++j) rw[(tgt1 ? NW : 0) + j] = u[j];
+                    if (fix_pos >= 0) ub[fix_pos] = (uint8_t)fix_val;
                 }
             }
+        } else {
+            // ---- packed path: concatenations, and everything for untrusted / non-cyclic rows ----
+            uint32_t w0[NW], w1[NW];
+            const uint2* rp = reinterpret_cast<const uint2*>(rw);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const uint2 v = rp[j];
+                const int a = 2 * j, b = 2 * j + 1;
+                if (a < NW) w0[a] = v.x; else w1[a - NW] = v.x;
+                if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
+            }
+            Rel<N> r0 = pack_words<NW, N>(w0);
+            Rel<N> r1 = pack_words<NW, N>(w1);
+            if (act > 11) {
+                status = ST_ASSERT;  // ac_moves.py:188-190
+            } else {
+                bool changed_other = false;
+                status = apply_move<N, TRUSTED>(r0, r1, act, 4 * NW, P.cyclical != 0, changed_other);
+                if (status == ST_OK) {
+                    const bool tgt1 = ((act + 1) & 1) != 0;
+                    Rel<N> t;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) t.b.w[j] = tgt1 ? r1.b.w[j] : r0.b.w[j];
+                    t.len = tgt1 ? r1.len : r0.len;
+                    store_relator<NW, N>(rw + (tgt1 ? NW : 0), t);
+                    if (!TRUSTED && changed_other)  // only for caller-supplied, not yet normalised rows
+                        store_relator<NW, N>(rw + (tgt1 ? 0 : NW), tgt1 ? r0 : r1);
+                }
+            }
+            len0 = r0.len;
+            len1 = r1.len;
         }
-        write_row_outputs(P, row, o);
+        s_res[r] = ((uint32_t)status << 16) | ((uint32_t)len0 << 8) | (uint32_t)len1;
     }
-    tile_store(smem, P, row0, nrows, bulk);
+    tile_store(smem, P, row0, nrows, bulk);  // fence + __syncthreads inside: s_res is visible after it
+
+    if (active) {  // coalesced per-row outputs by the owner of the row index
+        const uint32_t res = s_res[tid];
+        const int status = (int)(res >> 16), l0 = (int)((res >> 8) & 0xFF), l1 = (int)(res & 0xFF);
+        if (status != ST_OK) {
+            if (P.status) P.status[row] = (uint8_t)status;
+            if (P.err) {
+                atomicAdd((unsigned long long*)&P.err[0], 1ull);
+                atomicMin((unsigned long long*)&P.err[1], (unsigned long long)row);
+            }
+        } else {  // a raising row keeps its state, counters and rewards untouched
+            if (P.status) P.status[row] = 0;
+            if (P.lens) reinterpret_cast<uchar2*>(P.lens)[row] = make_uchar2((uint8_t)l0, (uint8_t)l1);
+            if (P.reward) {  // ac_env.py:101-105
+                const int tot = l0 + l1;
+                const bool d = tot == 2;
+                P.reward[row] = d ? P.max_reward : -tot;
+                P.done[row] = (uint8_t)d;
+                P.step_count[row] = sc + 1;
+                P.truncated[row] = (uint8_t)(sc + 1 >= P.horizon);
+            }
+        }
+    }
 }
 
 // ---- generic kernel: any mrl <= 64, byte accesses to the staged tile -----------------
-template <int W>
+template <int N, bool TRUSTED>
 __global__ void __launch_bounds__(kTileRows, 8) ac_step_bytes_kernel(const StepParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -267,21 +308,21 @@ __global__ void __launch_bounds__(kTileRows, 8) ac_step_bytes_kernel(const StepP
     else __syncthreads();
     if (active) {
         int8_t* rp = reinterpret_cast<int8_t*>(smem) + (size_t)threadIdx.x * rowb;
-        Rel<W> r0 = pack_bytes<W>(rp, P.mrl);
-        Rel<W> r1 = pack_bytes<W>(rp + P.mrl, P.mrl);
+        Rel<N> r0 = pack_bytes<N>(rp, P.mrl);
+        Rel<N> r1 = pack_bytes<N>(rp + P.mrl, P.mrl);
         RowOut o;
         if (action > 11) {
             o.status = ST_ASSERT;
             o.len0 = o.len1 = 0;
         } else {
             bool changed_other = false;
-            o.status = apply_move<W>(r0, r1, action, P.mrl, P.cyclical != 0, changed_other);
+            o.status = apply_move<N, TRUSTED>(r0, r1, action, P.mrl, P.cyclical != 0, changed_other);
             o.len0 = r0.len;
             o.len1 = r1.len;
             if (o.status == ST_OK) {
                 const bool tgt1 = ((action + 1) & 1) != 0;
-                if (tgt1 || changed_other) unpack_bytes<W>(rp + P.mrl, r1, P.mrl);
-                if (!tgt1 || changed_other) unpack_bytes<W>(rp, r0, P.mrl);
+                if (tgt1 || changed_other) unpack_bytes<N>(rp + P.mrl, r1, P.mrl);
+                if (!tgt1 || changed_other) unpack_bytes<N>(rp, r0, P.mrl);
             }
         }
         write_row_outputs(P, row, o);
@@ -291,10 +332,19 @@ __global__ void __launch_bounds__(kTileRows, 8) ac_step_bytes_kernel(const StepP
 
 template <int NW>
 static cudaError_t launch_words(const StepParams& P, cudaStream_t s) {
-    constexpr int W = NW <= 8 ? 1 : 2;
     const int64_t tiles = (P.n + kTileRows - 1) / kTileRows;
     const size_t smem = (size_t)kTileRows * 8 * NW;
-    ac_step_words_kernel<NW, W><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
+    if (P.trusted) ac_step_words_kernel<NW, true><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
+    else ac_step_words_kernel<NW, false><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+template <int N>
+static cudaError_t launch_bytes(const StepParams& P, cudaStream_t s) {
+    const int64_t tiles = (P.n + kTileRows - 1) / kTileRows;
+    const size_t smem = (size_t)kTileRows * 2 * P.mrl;
+    if (P.trusted) ac_step_bytes_kernel<N, true><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
+    else ac_step_bytes_kernel<N, false><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
     return cudaGetLastError();
 }
 
@@ -303,18 +353,21 @@ cudaError_t launch_step(const StepParams& P, cudaStream_t s) {
     if (P.mrl < 1 || P.mrl > 64) return cudaErrorInvalidValue;
     if (P.mrl % 4 == 0) {
         switch (P.mrl / 4) {
-#define ACS_CASE(k) case k: return launch_words<k>(P, s);
+#define ACS_CASE(k) \
+    case k:         \
+        return launch_words<k>(P, s);
             ACS_CASE(1) ACS_CASE(2) ACS_CASE(3) ACS_CASE(4) ACS_CASE(5) ACS_CASE(6) ACS_CASE(7) ACS_CASE(8)
             ACS_CASE(9) ACS_CASE(10) ACS_CASE(11) ACS_CASE(12) ACS_CASE(13) ACS_CASE(14) ACS_CASE(15)
             ACS_CASE(16)
 #undef ACS_CASE
         }
     }
-    const int64_t tiles = (P.n + kTileRows - 1) / kTileRows;
-    const size_t smem = (size_t)kTileRows * 2 * P.mrl;
-    if (P.mrl <= 32) ac_step_bytes_kernel<1><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
-    else ac_step_bytes_kernel<2><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
-    return cudaGetLastError();
+    switch (words_for(P.mrl)) {
+        case 1: return launch_bytes<1>(P, s);
+        case 2: return launch_bytes<2>(P, s);
+        case 3: return launch_bytes<3>(P, s);
+        default: return launch_bytes<4>(P, s);
+    }
 }
 
 }  // namespace acs

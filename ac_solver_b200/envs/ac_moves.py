@@ -58,14 +58,16 @@ def ACMove(move_id, presentation, max_relator_length, lengths, cyclical=True):
     return out[0].astype(p.dtype), [int(aux[0, 0]), int(aux[0, 1])]
 
 
-def ac_moves_batch(states, actions, cyclical=True, validate=True, device=None):
+def ac_moves_batch(states, actions, cyclical=True, validate=True, normalized=False, device=None):
     """Batched ACMove over HOST arrays: states [N, 2*mrl] int8, actions [N] in 0..11 ->
     (next_states int8 [N, 2*mrl], lengths uint8 [N,2], status uint8 [N]).
 
     status[k] != 0 marks rows for which the reference raises (1 AssertionError, 2 IndexError);
     those rows are returned unchanged.  Runs the packed kernel through ``acs_moves_batch_host``
     (chunked H2D -> kernel -> D2H pipeline).  ``validate`` checks once, on the GPU, that rows
-    are right-padded words over {+-1,+-2}."""
+    are right-padded words over {+-1,+-2}.  ``normalized=True`` promises that every word is
+    already a normal form for ``cyclical`` (as all outputs of this function are) and selects
+    the steady-state kernel variant that skips re-simplifying the untouched relator."""
     L = _lib.lib()
     ctx = _lib.ctx(_lib.default_device() if device is None else device)
     s = _i8(states)
@@ -85,6 +87,7 @@ def ac_moves_batch(states, actions, cyclical=True, validate=True, device=None):
     status = np.zeros(n, np.uint8)
     _lib.check(
         L.acs_moves_batch_host(ctx, s.ctypes.data, a.ctypes.data, out.ctypes.data, lens.ctypes.data,
-                               status.ctypes.data, n, w // 2, int(bool(cyclical)))
+                               status.ctypes.data, n, w // 2,
+                               (_lib.FLAG_CYCLICAL if cyclical else 0) | (_lib.FLAG_NORMALIZED if normalized else 0))
     )
     return out, lens, status

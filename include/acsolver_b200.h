@@ -67,26 +67,34 @@ void acs_ctx_destroy(acs_ctx *ctx);
 
 /* ---- ACMove, batched (envs/ac_moves.py:159-231) --------------------------------- */
 /* out may alias in.  lens [n,2] (recomputed lengths), status [n], err (two uint64:
- * number of non-OK rows, smallest such row; must be initialised to {0, ~0}) may be NULL. */
+ * number of non-OK rows, smallest such row; must be initialised to {0, ~0}) may be NULL.
+ * flags: ACS_FLAG_CYCLICAL = ACMove's `cyclical` argument; ACS_FLAG_NORMALIZED = the caller
+ * guarantees every input word is already a normal form for that cyclical flag (freely
+ * reduced, and cyclically reduced if cyclical) -- true for any state this library produced
+ * with the same flag -- which lets the kernel skip re-validating the untouched relator. */
+#define ACS_FLAG_CYCLICAL 1
+#define ACS_FLAG_NORMALIZED 2
 int acs_moves_batch(const int8_t *d_in, const uint8_t *d_action, int8_t *d_out, uint8_t *d_lens,
-                    uint8_t *d_status, uint64_t *d_err, int64_t n, int mrl, int cyclical, void *stream);
+                    uint8_t *d_status, uint64_t *d_err, int64_t n, int mrl, int flags, void *stream);
 int acs_moves_batch_host(acs_ctx *ctx, const int8_t *h_in, const uint8_t *h_action, int8_t *h_out,
-                         uint8_t *h_lens, uint8_t *h_status, int64_t n, int mrl, int cyclical);
+                         uint8_t *h_lens, uint8_t *h_status, int64_t n, int mrl, int flags);
 
 /* ---- ACEnv.step, batched (envs/ac_env.py:95-113) --------------------------------- */
 /* n independent environments; state [n,2*mrl] updated in place (cyclical=True as in the
  * reference); reward = horizon*mrl*2 if done else -(len0+len1); step_count += 1;
- * truncated = step_count >= horizon.  d_lens / d_status / d_err may be NULL. */
+ * truncated = step_count >= horizon.  d_lens / d_status / d_err may be NULL.
+ * flags: ACS_FLAG_NORMALIZED as above (every state after an environment's first step is
+ * normalized; pass it unless a reset just planted caller-supplied states). */
 int acs_env_step_batch(int8_t *d_state, const uint8_t *d_action, int32_t *d_reward, uint8_t *d_done,
                        uint8_t *d_truncated, int32_t *d_step_count, uint8_t *d_lens, uint8_t *d_status,
-                       uint64_t *d_err, int64_t n, int mrl, int horizon, void *stream);
+                       uint64_t *d_err, int64_t n, int mrl, int horizon, int flags, void *stream);
 /* Same step with the environment state RESIDENT on the device (d_state, d_step_count
  * owned by the caller) and host actions in / host observations, rewards and flags out:
  * the vector-env call of agents/training.py:154-156.  h_obs may be NULL (observations
  * stay on the device).  *n_bad receives the number of rows whose move raised. */
 int acs_env_step_host(acs_ctx *ctx, int8_t *d_state, int32_t *d_step_count, const uint8_t *h_action,
                       int8_t *h_obs, int32_t *h_reward, uint8_t *h_done, uint8_t *h_truncated,
-                      int64_t n, int mrl, int horizon, int64_t *n_bad);
+                      int64_t n, int mrl, int horizon, int flags, int64_t *n_bad);
 
 /* ---- boundary validation (envs/utils.py:13-54) ------------------------------------ */
 /* flags[row]: bit0 is_array_valid_presentation, bit1 letters in {0,+-1,+-2},

@@ -63,6 +63,28 @@ def test_moves_batch_vs_oracle(mrl, n, cyclical):
     assert np.array_equal(lens[ok], el[ok])
 
 
+@pytest.mark.parametrize("mrl,n", [(36, 300_000), (24, 100_000), (28, 50_000), (7, 50_000), (18, 50_000), (61, 20_000), (16, 20_000), (3, 5000)])
+@pytest.mark.parametrize("cyclical", [True, False])
+def test_moves_batch_normalized_variant(mrl, n, cyclical):
+    """The steady-state kernel variant (ACS_FLAG_NORMALIZED) on normal-form inputs, chained
+    for several steps so that its own outputs feed it again: bit-exact vs the oracle."""
+    from ac_solver_b200 import ac_moves_batch
+
+    rng = np.random.default_rng(2000 + mrl)
+    S = random_rows(rng, n, mrl, reduced=True)  # freely and cyclically reduced
+    if mrl >= 8:  # exercise rejection / long words: half the rows near the maximum length
+        S[: n // 2] = random_rows(rng, n // 2, mrl, reduced=True, min_len=max(1, mrl - 3))
+    for step in range(4):
+        A = rng.integers(0, 12, size=n).astype(np.uint8)
+        out, lens, status = ac_moves_batch(S, A, cyclical=cyclical, normalized=True, validate=False)
+        eo, el, es = O.moves_batch(S, A, cyclical=cyclical)
+        assert np.array_equal(status, es)
+        assert np.array_equal(out, eo)
+        ok = es == 0
+        assert np.array_equal(lens[ok], el[ok])
+        S = out
+
+
 def test_moves_batch_edge_cases():
     from ac_solver_b200 import ac_moves_batch
 
@@ -161,6 +183,7 @@ def test_env_step_batch_vs_oracle():
         A = rng.integers(0, 12, size=n).astype(np.uint8)
         _lib.check(L.acs_env_step_host(ctx, d_state.data_ptr(), d_sc.data_ptr(), A.ctypes.data, obs.ctypes.data,
                                        rew.ctypes.data, done.ctypes.data, trunc.ctypes.data, n, mrl, H,
+                                       2 if step >= 30 else 0,  # both kernel variants (states are normalized)
                                        C.byref(nbad)))
         er, ed, et, el, es = O.env_step_batch(ref_state, A, ref_sc, H)
         ok = es == 0
