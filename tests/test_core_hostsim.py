@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests import hostsim
+import hostsim
 from ac_solver_b200.synthetic import random_presentations
 
 
