@@ -26,7 +26,7 @@ for r in rows:
     if r[0] == "Line No":
         hdr = r
         continue
-    if hdr and len(r) == len(hdr) and r[0].isdigit() and kernel_seen == 1:
+    if hdr and len(r) == len(hdr) and r[0].isdigit():
         i_exec = hdr.index("Instructions Executed")
         i_samp = hdr.index("# Samples")
         key = (cur_file, int(r[0]))
@@ -35,5 +35,10 @@ for r in rows:
         per_line[key][2] = r[1].strip()[:90]
 tot = sum(v[0] for v in per_line.values())
 print(f"total warp-instructions attributed: {tot}")
-for (f, ln), v in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:45]:
+import collections
+byfile = collections.Counter()
+for (f, ln), v in per_line.items():
+    byfile[f] += v[0]
+print(dict(byfile))
+for (f, ln), v in sorted(per_line.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[2]) if len(sys.argv) > 2 else 45]:
     print(f"{v[0]:10d} {100*v[0]/tot:5.1f}%  samples {v[1]:5d}  {f}:{ln}  {v[2]}")
