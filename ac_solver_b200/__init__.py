@@ -9,6 +9,8 @@ importing the package needs no GPU, calling a compute function does (no CPU fall
 from .envs.ac_env import ACEnv, ACEnvConfig  # noqa: F401
 from .envs.ac_moves import ACMove, ac_moves_batch, concatenate_relators, conjugate  # noqa: F401
 from .search.breadth_first import bfs  # noqa: F401
+from .search.greedy import greedy_search, greedy_search_batch  # noqa: F401
 
-__all__ = ["ACEnv", "ACEnvConfig", "ACMove", "ac_moves_batch", "bfs", "concatenate_relators", "conjugate"]
+__all__ = ["ACEnv", "ACEnvConfig", "ACMove", "ac_moves_batch", "bfs", "greedy_search", "greedy_search_batch",
+           "concatenate_relators", "conjugate"]
 __version__ = "0.1.0"

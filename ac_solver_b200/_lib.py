@@ -64,6 +64,10 @@ _SIGS = {
     "acs_bfs_run": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(SearchResult)]),
     "acs_bfs_visited": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "acs_bfs_destroy": (None, [_P]),
+    "acs_greedy_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.POINTER(_P)]),
+    "acs_greedy_run": (C.c_int, [_P, _P, _P, _P]),
+    "acs_greedy_visited": (C.c_int, [_P, C.c_int, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "acs_greedy_destroy": (None, [_P]),
 }
 
 

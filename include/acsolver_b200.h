@@ -140,6 +140,18 @@ int acs_bfs_run(acs_bfs *b, const int8_t *h_presentation, int32_t *h_path, int p
 int acs_bfs_visited(acs_bfs *b, int8_t *h_out, int64_t cap_rows, int64_t *n_out);
 void acs_bfs_destroy(acs_bfs *b);
 
+/* Batched greedy search (search/greedy.py:15-121): n_search independent presentations of the
+ * same mrl, one warp each, one launch.  h_presentations [n_search, 2*mrl]; h_paths
+ * [n_search, path_cap, 2] int32 (action, total_length) pairs; results [n_search].  On failure
+ * the path is the reference's `path + [(11, len)]` of the last popped node.  max_nodes < 2^24.
+ * Device memory: n_search * (max_nodes+16) * (16|32 + 8 + 4 + 8) B + the tables. */
+typedef struct acs_greedy acs_greedy;
+int acs_greedy_create(int device, int n_search, int mrl, int64_t max_nodes, int cyclical, int path_cap,
+                      acs_greedy **out);
+int acs_greedy_run(acs_greedy *g, const int8_t *h_presentations, int32_t *h_paths, acs_search_result *results);
+int acs_greedy_visited(acs_greedy *g, int search, int8_t *h_out, int64_t cap_rows, int64_t *n_out);
+void acs_greedy_destroy(acs_greedy *g);
+
 #ifdef __cplusplus
 }
 #endif

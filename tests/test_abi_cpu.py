@@ -1,0 +1,91 @@
+"""CPU-side checks of the boundary: the shared library loads without a GPU, exports every
+symbol include/acsolver_b200.h declares, and compute entry points fail loudly (no fallback)."""
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "acsolver_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(acs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ac_solver_b200 import _lib
+    from ac_solver_b200.build import build
+
+    build()
+    L = C.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    # the ctypes signature table covers the same set
+    assert sorted(_lib.exported_symbols()) == names
+    assert _lib.lib().acs_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    from ac_solver_b200 import ACMove, _lib, ac_moves_batch, bfs, greedy_search
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the loud-failure path is for CPU-only hosts")
+    ak2 = np.array([1, 1, -2, -2, -2, 0, 0, 1, 2, 1, -2, -1, -2, 0])
+    with pytest.raises(_lib.AcsError):
+        ACMove(0, ak2, 7, [5, 6])
+    with pytest.raises(_lib.AcsError):
+        ac_moves_batch(ak2[None, :].astype(np.int8), np.zeros(1, np.uint8))
+    with pytest.raises(_lib.AcsError):
+        bfs(ak2, 100)
+    with pytest.raises(_lib.AcsError):
+        greedy_search(ak2, 100)
+
+
+def test_host_helpers_match_reference_vectors(unit_vectors):
+    """Pure host logic (predicates / layout converters), reference tests/test_ac_env.py:86-137
+    and tests/envs/test_envs_utils.py:6-14."""
+    from ac_solver_b200.envs.utils import (change_max_relator_length_of_presentation,
+                                           convert_relators_to_presentation, generate_trivial_states,
+                                           is_array_valid_presentation, is_presentation_trivial)
+
+    for c in unit_vectors["is_array_valid_presentation"]:
+        assert is_array_valid_presentation(np.array(c["presentation"])) == c["expected"], c
+    for c in unit_vectors["is_presentation_trivial"]:
+        assert is_presentation_trivial(np.array(c["presentation"])) == c["expected"], c
+    for m in (1, 2, 3, 4):
+        st = generate_trivial_states(m)
+        assert st.shape == (8, 2 * m)
+        for s in st:
+            assert np.count_nonzero(s) == 2 and abs(s[0]) != abs(s[m]) and s[0] != 0 and s[m] != 0
+    ak2 = convert_relators_to_presentation([1, 1, -2, -2, -2], [1, 2, 1, -2, -1, -2], 7)
+    assert ak2.dtype == np.int8
+    assert ak2.tolist() == [1, 1, -2, -2, -2, 0, 0, 1, 2, 1, -2, -1, -2, 0]
+    wide = change_max_relator_length_of_presentation(ak2, 10)
+    assert wide.tolist() == [1, 1, -2, -2, -2, 0, 0, 0, 0, 0, 1, 2, 1, -2, -1, -2, 0, 0, 0, 0]
+
+
+def test_env_config_errors():
+    from ac_solver_b200 import ACEnv, ACEnvConfig
+
+    with pytest.raises(TypeError):
+        ACEnvConfig(initial_state=(1, 0, 2, 0))
+    with pytest.raises(ValueError):
+        ACEnvConfig(initial_state=np.array([[1, 0], [2, 0]]))
+    with pytest.raises(ValueError):
+        ACEnvConfig(initial_state=np.array([1, 0, 2]))
+    with pytest.raises(ValueError):
+        ACEnvConfig(initial_state=np.array([1, 0, 0, 0]))
+    with pytest.raises(NotImplementedError):
+        ACEnv(ACEnvConfig(use_supermoves=True))
+    cfg = ACEnvConfig.from_dict({"initial_state": [1, 1, 0, 2, 0, 0], "horizon_length": 7})
+    env = ACEnv(cfg)
+    assert env.max_relator_length == 3 and env.max_reward == 7 * 3 * 2 and env.lengths == [2, 1]
+    assert env.observation_space.shape == (6,) and env.action_space.n == 12
