@@ -38,6 +38,24 @@ class SearchResult(C.Structure):
     ]
 
 
+class SbfsArgs(C.Structure):
+    """Mirror of ``acs_sbfs_args`` (include/acsolver_b200.h)."""
+
+    _fields_ = [
+        ("keys", C.c_void_p), ("parent", C.c_void_p), ("gid", C.c_void_p), ("table", C.c_void_p),
+        ("tmask", C.c_uint64), ("n_local", C.c_int64), ("l0", C.c_int64), ("l1", C.c_int64),
+        ("head", C.c_int64), ("nparents", C.c_int64), ("n_nodes", C.c_int64), ("budget", C.c_int64),
+        ("limit", C.c_int64),
+        ("mrl", C.c_int32), ("cyclical", C.c_int32), ("trusted", C.c_int32), ("world", C.c_int32),
+        ("rank", C.c_int32), ("min_len", C.c_int32), ("W", C.c_int32), ("pad_", C.c_int32),
+        ("dest_count", C.c_void_p), ("dest_cursor", C.c_void_p), ("send_keys", C.c_void_p),
+        ("send_c", C.c_void_p), ("ctrl", C.c_void_p), ("recv_keys", C.c_void_p), ("recv_c", C.c_void_p),
+        ("n_recv", C.c_int64), ("rec_slot", C.c_void_p), ("bitmap_local", C.c_void_p),
+        ("bitmap_global", C.c_void_p), ("prefix_local", C.c_void_p), ("prefix_global", C.c_void_p),
+        ("cut", C.c_void_p),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -68,6 +86,17 @@ _SIGS = {
     "acs_greedy_run": (C.c_int, [_P, _P, _P, _P]),
     "acs_greedy_visited": (C.c_int, [_P, C.c_int, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "acs_greedy_destroy": (None, [_P]),
+    "acs_sbfs_pack_root": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "acs_sbfs_owner": (C.c_int, [C.c_uint64, C.c_int]),
+    "acs_sbfs_expand": (C.c_int, [_P, C.c_int, _P]),
+    "acs_sbfs_insert_mark": (C.c_int, [_P, _P]),
+    "acs_sbfs_scan": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "acs_sbfs_cut": (C.c_int, [_P, _P]),
+    "acs_sbfs_rank_at": (C.c_int, [_P, _P, _P]),
+    "acs_sbfs_commit": (C.c_int, [_P, _P]),
+    "acs_sbfs_lower_bound": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
+    "acs_sbfs_lookup": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "acs_sbfs_unpack": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
 }
 
 

@@ -152,6 +152,52 @@ int acs_greedy_run(acs_greedy *g, const int8_t *h_presentations, int32_t *h_path
 int acs_greedy_visited(acs_greedy *g, int search, int8_t *h_out, int64_t cap_rows, int64_t *n_out);
 void acs_greedy_destroy(acs_greedy *g);
 
+/* ---- hash-partitioned multi-GPU BFS: per-rank device kernels --------------------------------- */
+/* The host loop (ac_solver_b200/search/sharded.py, one process per GPU, torch.distributed/NCCL
+ * for the all-to-all and the small all-reduces) drives these on caller-allocated device buffers.
+ * Same sequential contract as acs_bfs_run for every world size.  All pointers are DEVICE
+ * pointers; every call is asynchronous on `stream`. */
+typedef struct {
+    uint64_t *keys;      /* [cap][2W] owned nodes, increasing global id                     */
+    int64_t *parent;     /* [cap] (parent global id << 4 | action), root -1                 */
+    int64_t *gid;        /* [cap] global id of each owned node                              */
+    uint64_t *table;     /* [tmask+1] visited table of this rank (zero-initialised)         */
+    uint64_t tmask;
+    int64_t n_local;     /* owned nodes committed so far                                    */
+    int64_t l0, l1;      /* local index range of this chunk's parents                       */
+    int64_t head;        /* global id of the chunk's first parent                           */
+    int64_t nparents;    /* parents in the chunk, all ranks together                        */
+    int64_t n_nodes;     /* global node count at chunk start                                */
+    int64_t budget;
+    int64_t limit;       /* commit: chunk-local candidate ids below this are appended       */
+    int32_t mrl, cyclical, trusted, world, rank, min_len, W, pad_;
+    unsigned long long *dest_count;  /* [world] records per destination (phase 0)           */
+    unsigned long long *dest_cursor; /* [world] running write offsets (phase 1)             */
+    uint64_t *send_keys; /* [n_send][2W]                                                    */
+    uint32_t *send_c;    /* [n_send] chunk-local candidate id                               */
+    unsigned long long *ctrl; /* [130] min-reduced: solving id, error id<<2|status, first_len[128] */
+    const uint64_t *recv_keys;
+    const uint32_t *recv_c;
+    int64_t n_recv;
+    uint32_t *rec_slot;  /* [n_recv] scratch                                                */
+    uint32_t *bitmap_local, *bitmap_global; /* [ceil(12*nparents/32)] winner bits           */
+    uint32_t *prefix_local, *prefix_global; /* [words+1] exclusive popcount prefixes        */
+    unsigned long long *cut; /* [1] min chunk-local parent at which the budget is reached   */
+} acs_sbfs_args;
+
+int acs_sbfs_pack_root(const int8_t *h_presentation, int mrl, uint64_t *key_out4, uint64_t *hash_out,
+                       int *total_len, int *valid);
+int acs_sbfs_owner(uint64_t hash, int world);
+int acs_sbfs_expand(const acs_sbfs_args *a, int phase, void *stream);
+int acs_sbfs_insert_mark(const acs_sbfs_args *a, void *stream);
+int acs_sbfs_scan(const uint32_t *d_bitmap, uint32_t *d_prefix, int64_t nwords, void *stream);
+int acs_sbfs_cut(const acs_sbfs_args *a, void *stream);
+int acs_sbfs_rank_at(const acs_sbfs_args *a, uint64_t *d_out2, void *stream);
+int acs_sbfs_commit(const acs_sbfs_args *a, void *stream);
+int acs_sbfs_lower_bound(const int64_t *d_gid, int64_t n, int64_t value, int64_t *d_out, void *stream);
+int acs_sbfs_lookup(const acs_sbfs_args *a, int64_t gid, int64_t *d_out4, void *stream);
+int acs_sbfs_unpack(const uint64_t *d_keys, int8_t *d_out, int64_t n, int mrl, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
