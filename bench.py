@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--mrl", type=int, default=36)
     ap.add_argument("--cpu-sample-rows", type=int, default=1 << 17)
     ap.add_argument("--skip-bfs", action="store_true")
-    ap.add_argument("--bfs-budget", type=int, default=2_000_000)
+    ap.add_argument("--bfs-budget", type=int, default=100_000_000)
     return ap.parse_args()
 
 
@@ -179,7 +179,7 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
 
     from ac_solver_b200 import _lib
     from ac_solver_b200.synthetic import random_actions, random_presentations
@@ -270,9 +270,9 @@ def run_b200(args):
     sampler.join(timeout=2)
 
     bfs_line = None
-    if rank == 0 and not args.skip_bfs:
+    if not args.skip_bfs and (rank == 0 or world > 1):
         try:
-            bfs_line = bench_bfs(args)
+            bfs_line = bench_bfs(args, world, dist)
         except Exception as e:  # the search bench is auxiliary; never lose the headline line
             bfs_line = {"error": repr(e)}
 
@@ -307,7 +307,7 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_move": 4 * mrl + 6,
+                "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_move": 4 * mrl + 6,
                 "kernel": "acs::ac_step_words_kernel<9,2>" if mrl == 36 else "acs::ac_step_*_kernel",
                 "frac_of_nominal_8TBs": achieved / 8000.0,
             },
@@ -331,13 +331,48 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def bench_bfs(args):
-    """Secondary metric: BFS nodes expanded / s on AK(3), mrl 24 (BASELINE.json configs[4] at 1 GPU)."""
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the latest committed `ncu --set full` capture of
+    the step kernel (profiles/k1_step_r1_ncu_summary.json; cold-cache, the write-back of the last
+    tiles is still in L2 when the capture ends, so it reads below the algorithmic bytes)."""
     try:
-        from ac_solver_b200.search.breadth_first import bfs_device
-    except Exception as e:
-        return {"unavailable": repr(e)}
+        with open(os.path.join(ROOT, "profiles", "k1_step_r1_ncu_summary.json")) as f:
+            d = json.load(f)
+        m = d[sorted(d)[-1]]
+        return (float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])) * 1e6
+    except Exception:
+        return None
+
+
+def bench_bfs(args, world=1, dist=None):
+    """Secondary metric: BFS nodes expanded / s on AK(3), mrl 24 (BASELINE.json configs[4]).
+    One GPU: the single-device search (csrc/bfs.cu).  Several GPUs: the hash-partitioned search
+    with an NCCL all-to-all per chunk (search/sharded.py), same total budget (strong scaling)."""
     ak3 = np.array([1, 1, 1, -2, -2, -2, -2] + [0] * 17 + [1, 2, 1, -2, -1, -2] + [0] * 18, np.int8)
+    if world > 1:
+        import contextlib
+        import io
+
+        import torch
+        from ac_solver_b200.search.sharded import bfs_sharded
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            bfs_sharded(ak3, 1_000_000)  # warm
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            solved, path, info = bfs_sharded(ak3, args.bfs_budget)
+            torch.cuda.synchronize()
+            dist.barrier()
+        wall = time.perf_counter() - t0
+        return {
+            "metric": "BFS nodes expanded/sec", "nodes_expanded": info["n_expanded"], "visited": info["n_visited"],
+            "workload": f"sharded bfs AK(3) mrl 24 budget {args.bfs_budget}, {world} GPUs, hash-partitioned, "
+                        "NCCL all-to-all per chunk",
+            "levels": info["n_levels"], "expanded_per_s_wall": info["n_expanded"] / wall, "seconds_wall": wall,
+        }
+    from ac_solver_b200.search.breadth_first import bfs_device
+
     bfs_device(ak3, 100000)  # warm
     t0 = time.perf_counter()
     solved, path, info = bfs_device(ak3, args.bfs_budget)
