@@ -1,0 +1,168 @@
+"""GPU-resident vector environment -- batched stand-in for the ``gym.vector.SyncVectorEnv`` of
+``ACEnv`` instances that the reference's PPO rollout steps one environment at a time on the host
+(``ac_solver/agents/environment.py:60-127``, ``ac_solver/agents/training.py:154-228``).
+
+All environment state (presentations, step counters, action logs) lives on the GPU; one call of
+``step`` is one launch of the fused env-step kernel (``acs_env_step_batch``) plus a few small
+torch ops for the auto-reset.  Semantics follow gymnasium 0.28.1's ``SyncVectorEnv`` as used by
+the reference: when an environment terminates or truncates it is reset to its own initial state,
+the returned observation is the reset observation, and ``infos["final_observation"]`` /
+``infos["final_info"]`` (with ``{"actions": [...]}`` for solved episodes, ``ac_env.py:107-113``)
+carry the last step of the finished episode.  The reference's own tests do not pin these
+wrapper semantics; tests/test_vector_env_gpu.py pins them against a per-environment
+loop of the oracle's ``ACEnv.step``.
+
+Inputs decide the output container: numpy actions give numpy outputs (drop-in for
+``training.py``), a CUDA tensor gives CUDA tensors (rollouts that never leave the device).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib
+from .spaces import Box, Discrete
+from .utils import is_array_valid_presentation
+
+
+class _EnvProxy:
+    """``envs.envs[i]``: the two things the PPO loop touches (training.py:224,233)."""
+
+    def __init__(self, owner, index):
+        self._owner, self._index = owner, index
+
+    @property
+    def max_reward(self):
+        return self._owner.max_reward
+
+    @property
+    def state(self):
+        return self._owner.state[self._index].cpu().numpy()
+
+    def reset(self, *, seed=None, options=None):
+        """ac_env.py:115-131 for one environment (``options["starting_state"]`` honoured)."""
+        o = self._owner
+        src = options["starting_state"] if options and "starting_state" in options else o.initial_states_host[self._index]
+        o.set_states([self._index], np.asarray(src)[None, :])
+        return np.array(src, dtype=np.int8), {}
+
+
+class ACVectorEnv:
+    def __init__(self, initial_states, horizon_length=1000, device=None, clip_rewards=None, use_supermoves=False):
+        """initial_states: [N, 2*mrl] presentations (one per environment), all valid
+        (``ACEnvConfig.__post_init__``, ac_env.py:22-35).  clip_rewards: optional (min, max) as in
+        ``TransformReward(np.clip)`` (environment.py:48-52)."""
+        import torch
+
+        if use_supermoves:
+            raise NotImplementedError("ACEnv with supermoves is not yet implemented in this library.")
+        init = np.asarray(initial_states)
+        if init.ndim != 2 or init.shape[1] % 2:
+            raise ValueError("initial_states must be [num_envs, 2*max_relator_length]")
+        for row in init:
+            if not is_array_valid_presentation(row):
+                raise ValueError("initial state must be a valid presentation")
+        if np.abs(init).max() > 2:
+            raise ValueError("the GPU environment supports the two-generator alphabet {+-1, +-2} only")
+        if not torch.cuda.is_available():
+            raise _lib.AcsError("no CUDA device visible; ACVectorEnv has no CPU fallback")
+        self.torch = torch
+        self.L = _lib.lib()
+        self.dev = torch.device("cuda", _lib.default_device() if device is None else device)
+        self.num_envs, width = init.shape
+        self.max_relator_length = width // 2
+        self.horizon_length = int(horizon_length)
+        self.max_reward = self.horizon_length * self.max_relator_length * 2  # ac_env.py:80
+        self.clip_rewards = clip_rewards
+        bound = np.full(width, 2, dtype=np.int8)
+        self.single_observation_space = Box(-bound, bound, dtype=np.int8)
+        self.single_action_space = Discrete(12)
+        self.initial_states_host = init.astype(np.int8)
+        self.initial_states = torch.from_numpy(self.initial_states_host).to(self.dev)
+        n = self.num_envs
+        self.state = self.initial_states.clone()
+        self.step_count = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        self.reward = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        self.truncated = torch.zeros(n, dtype=torch.uint8, device=self.dev)
+        self.action_log = torch.zeros((n, max(self.horizon_length, 1)), dtype=torch.uint8, device=self.dev)
+        self.err = torch.tensor([0, -1], dtype=torch.int64, device=self.dev)
+        self._rows = torch.arange(n, device=self.dev)
+        # caller-supplied states may be non-reduced: the first step after a (re)set runs the general
+        # kernel variant; states produced by the kernel are normal forms (ACS_FLAG_NORMALIZED).
+        self._normalized = False
+        self.envs = [_EnvProxy(self, i) for i in range(n)]
+
+    # ---------------------------------------------------------------------------------------
+    def set_states(self, indices, states):
+        """Plant caller-supplied presentations into the given environments (per-env ``reset`` with
+        ``starting_state``; the curriculum hook of training.py:223-224), resetting their counters."""
+        t = self.torch
+        s = np.ascontiguousarray(states, dtype=np.int8)
+        for row in s:
+            assert is_array_valid_presentation(row), f"{row} is not a valid presentation"
+        idx = t.as_tensor(np.asarray(indices, dtype=np.int64), device=self.dev)
+        self.state[idx] = t.from_numpy(s).to(self.dev)
+        self.step_count[idx] = 0
+        self._normalized = False
+
+    def reset(self, *, seed=None, options=None):
+        """All environments back to their initial states -> (obs, {})."""
+        self.state.copy_(self.initial_states)
+        self.step_count.zero_()
+        self._normalized = False
+        return self.state.cpu().numpy(), {}
+
+    def step(self, actions):
+        t = self.torch
+        as_numpy = not isinstance(actions, t.Tensor)
+        act = t.as_tensor(np.ascontiguousarray(actions, dtype=np.uint8) if as_numpy else actions).to(
+            device=self.dev, dtype=t.uint8).contiguous()
+        if act.shape != (self.num_envs,):
+            raise ValueError("actions must have shape (num_envs,)")
+        # log the action at the pre-step counter (info["actions"] of a finished episode)
+        pos = self.step_count.to(t.int64).clamp_(max=self.action_log.shape[1] - 1)
+        self.action_log[self._rows, pos] = act
+        self.err[0], self.err[1] = 0, -1
+        flags = _lib.FLAG_NORMALIZED if self._normalized else 0
+        stream = t.cuda.current_stream(self.dev).cuda_stream
+        _lib.check(self.L.acs_env_step_batch(
+            self.state.data_ptr(), act.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+            self.truncated.data_ptr(), self.step_count.data_ptr(), None, None, self.err.data_ptr(),
+            self.num_envs, self.max_relator_length, self.horizon_length, flags, stream))
+        self._normalized = True
+        finished = (self.done | self.truncated).bool()
+        n_bad, any_fin = (int(v) for v in t.stack([self.err[0], finished.any().to(t.int64)]).cpu())
+        if n_bad:
+            raise AssertionError(f"{n_bad} environments produced an invalid presentation (first: env {int(self.err[1])}); "
+                                 "the reference raises AssertionError here (envs/utils.py:261-263)")
+        reward = self.reward.to(t.float64)
+        if self.clip_rewards is not None:
+            reward = reward.clamp(self.clip_rewards[0], self.clip_rewards[1])
+        infos = {}
+        obs = self.state
+        if any_fin:
+            fin_idx = finished.nonzero().flatten()
+            final_obs = self.state[fin_idx].cpu().numpy()
+            lens = self.step_count[fin_idx].cpu().numpy()
+            logs = self.action_log[fin_idx].cpu().numpy()
+            solved = self.done[fin_idx].cpu().numpy().astype(bool)
+            fo = np.full(self.num_envs, None, dtype=object)
+            fi = np.full(self.num_envs, None, dtype=object)
+            mask = np.zeros(self.num_envs, dtype=bool)
+            for k, i in enumerate(fin_idx.cpu().numpy()):
+                fo[i] = final_obs[k]
+                fi[i] = {"actions": [int(a) for a in logs[k, : lens[k]]]} if solved[k] else {}
+                mask[i] = True
+            infos = {"final_observation": fo, "_final_observation": mask, "final_info": fi, "_final_info": mask.copy()}
+            # auto-reset: the env's own initial state, counters zeroed (gymnasium SyncVectorEnv)
+            self.state[fin_idx] = self.initial_states[fin_idx]
+            self.step_count[fin_idx] = 0
+            self._normalized = False
+        if as_numpy:
+            return (obs.cpu().numpy(), reward.cpu().numpy(), self.done.cpu().numpy().astype(bool),
+                    self.truncated.cpu().numpy().astype(bool), infos)
+        return obs.clone(), reward, self.done.bool(), self.truncated.bool(), infos
+
+    def close(self):
+        pass
