@@ -14,6 +14,9 @@
 //     int8 with a PRMT table lookup, and only the REWRITTEN relator is stored back;
 //   * reward / done / truncated / step counter are fused into the same pass.
 #include <cstdint>
+#include <cstdlib>
+#include <type_traits>
+
 #include <cuda_runtime.h>
 
 #include "ac_core.cuh"
@@ -147,20 +150,20 @@ __device__ __forceinline__ void store_relator(uint32_t* wp, const Rel<N>& t) {
 // of uniformly random moves never enter the packed domain.  Per-row results are staged in
 // shared memory and written back by the thread that owns the row index, so every global
 // access stays coalesced.
-template <int NW, bool TRUSTED>
-__global__ void __launch_bounds__(kTileRows, 8) ac_step_words_kernel(const StepParams P) {
+template <int NW, bool TRUSTED, int TR>
+__global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(const StepParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint8_t s_perm[kTileRows];
-    __shared__ uint8_t s_act[kTileRows];
-    __shared__ uint32_t s_res[kTileRows];  // status << 16 | len0 << 8 | len1
-    __shared__ int s_wcnt[kTileRows / 32];
+    __shared__ uint8_t s_perm[TR];
+    __shared__ uint8_t s_act[TR];
+    __shared__ uint32_t s_res[TR];  // status << 16 | len0 << 8 | len1
+    __shared__ int s_wcnt[TR / 32];
     constexpr int N = (NW + 3) / 4;
     constexpr int ROWB = 8 * NW;  // bytes per row
     const int tid = threadIdx.x;
-    const int64_t row0 = (int64_t)blockIdx.x * kTileRows;
-    const int nrows = (int)min((int64_t)kTileRows, P.n - row0);
-    const bool bulk = P.bulk_ok && nrows == kTileRows;
+    const int64_t row0 = (int64_t)blockIdx.x * TR;
+    const int nrows = (int)min((int64_t)TR, P.n - row0);
+    const bool bulk = P.bulk_ok && nrows == TR;
 
     if (bulk && tid == 0) {
         mbar_init(&bar, 1);
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(kTileRows, 8) ac_step_words_kernel(const StepP
     __syncthreads();
     int n0 = 0, before = __popc(bal & ((1u << lane) - 1u));
 #pragma unroll
-    for (int w = 0; w < kTileRows / 32; ++w) {
+    for (int w = 0; w < TR / 32; ++w) {
         const int c = s_wcnt[w];
         n0 += c;
         if (w < wid) before += c;
@@ -204,11 +207,19 @@ __global__ void __launch_bounds__(kTileRows, 8) ac_step_words_kernel(const StepP
         if (TRUSTED && P.cyclical && act >= 4 && act <= 11) {
             // ---- conjugation of a normal form: rotation in the byte domain ----
             const bool tgt1 = ((act + 1) & 1) != 0;
-            uint32_t u[NW], w[NW];
+            uint32_t w0[NW], w1[NW], u[NW], w[NW];
+            const uint2* rp = reinterpret_cast<const uint2*>(rw);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {  // 64-bit loads of the whole row: fewest LDS wavefronts
+                const uint2 v = rp[j];
+                const int a = 2 * j, b = 2 * j + 1;
+                if (a < NW) w0[a] = v.x; else w1[a - NW] = v.x;
+                if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
+            }
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
-                u[j] = rw[(tgt1 ? NW : 0) + j];
-                w[j] = rw[(tgt1 ? 0 : NW) + j];
+                u[j] = tgt1 ? w1[j] : w0[j];
+                w[j] = tgt1 ? w0[j] : w1[j];
             }
             const int lu = count_letters<NW>(u), lw = count_letters<NW>(w);
             len0 = tgt1 ? lw : lu;
@@ -332,10 +343,27 @@ __global__ void __launch_bounds__(kTileRows, 8) ac_step_bytes_kernel(const StepP
 
 template <int NW>
 static cudaError_t launch_words(const StepParams& P, cudaStream_t s) {
-    const int64_t tiles = (P.n + kTileRows - 1) / kTileRows;
-    const size_t smem = (size_t)kTileRows * 8 * NW;
-    if (P.trusted) ac_step_words_kernel<NW, true><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
-    else ac_step_words_kernel<NW, false><<<(unsigned)tiles, kTileRows, smem, s>>>(P);
+    // tile rows: 128 by default; ACS_TILE_ROWS=64|256 selects the tuning variants that are
+    // compiled for the headline width (mrl 36)
+    static const int tile_rows = [] {
+        const char* e = getenv("ACS_TILE_ROWS");
+        const int v = e ? atoi(e) : 128;
+        return (v == 64 || v == 256) ? v : 128;
+    }();
+    auto launch = [&](auto tr) {
+        constexpr int TR = decltype(tr)::value;
+        const int64_t tiles = (P.n + TR - 1) / TR;
+        const size_t smem = (size_t)TR * 8 * NW;
+        if (P.trusted) ac_step_words_kernel<NW, true, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
+        else ac_step_words_kernel<NW, false, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
+    };
+    if constexpr (NW == 9) {
+        if (tile_rows == 64) launch(std::integral_constant<int, 64>{});
+        else if (tile_rows == 256) launch(std::integral_constant<int, 256>{});
+        else launch(std::integral_constant<int, 128>{});
+    } else {
+        launch(std::integral_constant<int, 128>{});
+    }
     return cudaGetLastError();
 }
 
