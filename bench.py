@@ -53,6 +53,13 @@ def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -117,12 +124,12 @@ def cpu_baseline(rows, mrl, seconds_target=12.0):
     S = random_presentations(rows, mrl, seed=0)
     sc = np.zeros(rows, np.int32)
     A = random_actions(rows, seed=1)
-    threads = O.num_threads()
-    O.env_step_batch(S, A, sc, HORIZON)  # warm
+    threads = host_threads()  # torchrun pins OMP_NUM_THREADS=1: ask for every core explicitly
+    O.env_step_batch(S, A, sc, HORIZON, nthreads=threads)  # warm
     t0 = time.perf_counter()
     reps = 0
     while True:
-        O.env_step_batch(S, A, sc, HORIZON)
+        O.env_step_batch(S, A, sc, HORIZON, nthreads=threads)
         reps += 1
         if time.perf_counter() - t0 > seconds_target or reps >= 2000:
             break
@@ -147,12 +154,12 @@ def run_reference(args):
     S = random_presentations(rows, mrl, seed=0)
     A = random_actions(rows, seed=1)
     sc = np.zeros(rows, np.int32)
-    threads = O.num_threads()
+    threads = host_threads()  # torchrun pins OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(max(args.warmup, 1)):
-        O.env_step_batch(S, A, sc, HORIZON)
+        O.env_step_batch(S, A, sc, HORIZON, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.env_step_batch(S, A, sc, HORIZON)
+        O.env_step_batch(S, A, sc, HORIZON, nthreads=threads)
     dt = time.perf_counter() - t0
     v = rows * args.steps / dt
     sample = f"each step = ACEnv.step over a {rows}-row sample of the 1 Mi-row workload, C oracle on {threads} host threads"
