@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libacsolver_b200.so")
 ACS_OK = 0
 ROW_OK, ROW_ASSERT, ROW_INDEX = 0, 1, 2
 OP_ACMOVE, OP_CONCAT_RAW, OP_CONJ_RAW, OP_SIMPLIFY_RELATOR, OP_SIMPLIFY_PRESENTATION = range(5)
-FLAG_CYCLICAL, FLAG_NORMALIZED = 1, 2
+FLAG_CYCLICAL, FLAG_NORMALIZED, FLAG_LENS_VALID = 1, 2, 4
 
 
 class AcsError(RuntimeError):

@@ -25,7 +25,8 @@ __device__ __forceinline__ uint32_t gather4(uint32_t p0, uint32_t p1, uint32_t p
 }
 
 // NW int8 words (4*NW letters) -> packed relator of N = ceil(NW/4) code words
-template <int NW, int N>
+// COUNT = false skips the letter count (the caller knows the length and sets r.len).
+template <int NW, int N, bool COUNT = true>
 __device__ __forceinline__ Rel<N> pack_words(const uint32_t (&w)[NW]) {
     Rel<N> r;
     uint32_t nz = 0;  // per byte lane: 2 * (number of non-zero letters seen in that lane)
@@ -37,14 +38,14 @@ __device__ __forceinline__ Rel<N> pack_words(const uint32_t (&w)[NW]) {
             const int j = 4 * q + k;
             if (j < NW) {
                 p[k] = codes_top8(w[j]);
-                nz += (w[j] | (w[j] * 2u)) & 0x02020202u;  // letters are 0 or have bit0|bit1 set
+                if (COUNT) nz += (w[j] | (w[j] * 2u)) & 0x02020202u;  // letters are 0 or have bit0|bit1 set
             } else {
                 p[k] = 0;
             }
         }
         r.b.w[q] = gather4(p[0], p[1], p[2], p[3]);
     }
-    r.len = (int)((nz * 0x01010101u) >> 25);
+    r.len = COUNT ? (int)((nz * 0x01010101u) >> 25) : 0;
     return r;
 }
 

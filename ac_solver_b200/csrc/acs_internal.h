@@ -24,6 +24,7 @@ struct StepParams {
     int max_reward;
     int bulk_ok;            // in/out are 16-byte aligned: TMA bulk copies allowed
     int trusted;            // rows are normal forms for `cyclical` (see ac_core.cuh apply_move)
+    int lens_valid;         // `lens` holds the current relator lengths on entry (in/out)
 };
 
 // thread-local error text behind acs_last_error() (capi.cu)

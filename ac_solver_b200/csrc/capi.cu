@@ -130,6 +130,7 @@ int acs_moves_batch(const int8_t* d_in, const uint8_t* d_action, int8_t* d_out, 
     P.mrl = mrl;
     P.cyclical = (flags & ACS_FLAG_CYCLICAL) ? 1 : 0;
     P.trusted = (flags & ACS_FLAG_NORMALIZED) ? 1 : 0;
+    P.lens_valid = ((flags & ACS_FLAG_LENS_VALID) && P.trusted && d_lens) ? 1 : 0;
     P.bulk_ok = aligned16(d_in) && aligned16(d_out);
     ACS_CUDA(acs::launch_step(P, static_cast<cudaStream_t>(stream)));
     return ACS_OK;
@@ -156,6 +157,7 @@ int acs_env_step_batch(int8_t* d_state, const uint8_t* d_action, int32_t* d_rewa
     P.mrl = mrl;
     P.cyclical = 1;  // ac_env.py:97-99 uses ACMove's default cyclical=True
     P.trusted = (flags & ACS_FLAG_NORMALIZED) ? 1 : 0;
+    P.lens_valid = ((flags & ACS_FLAG_LENS_VALID) && P.trusted && d_lens) ? 1 : 0;
     P.horizon = horizon;
     P.max_reward = horizon * mrl * 2;  // ac_env.py:80
     P.bulk_ok = aligned16(d_state);

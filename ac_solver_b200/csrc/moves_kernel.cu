@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
     __shared__ uint8_t s_act[TR];
     __shared__ uint32_t s_res[TR];  // status << 16 | len0 << 8 | len1
     __shared__ int s_wcnt[TR / 32];
+    __shared__ uint16_t s_lens[TR];  // len0 | len1 << 8 on entry (ACS_FLAG_LENS_VALID)
     constexpr int N = (NW + 3) / 4;
     constexpr int ROWB = 8 * NW;  // bytes per row
     const int tid = threadIdx.x;
@@ -177,9 +178,11 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
     const bool active = tid < nrows;
     int action = 255;
     int sc = 0;
+    const bool have_lens = TRUSTED && P.lens_valid;  // lengths carried beside the state (ac_env.py:84-92)
     if (active) {
         action = P.action[row];
         if (P.reward) sc = P.step_count[row];
+        if (have_lens) s_lens[tid] = reinterpret_cast<const uint16_t*>(P.lens)[row];
     }
     const bool is_concat = active && !(action >= 4 && action <= 11);
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, is_concat);
@@ -207,21 +210,44 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
         if (TRUSTED && P.cyclical && act >= 4 && act <= 11) {
             // ---- conjugation of a normal form: rotation in the byte domain ----
             const bool tgt1 = ((act + 1) & 1) != 0;
-            uint32_t w0[NW], w1[NW], u[NW], w[NW];
-            const uint2* rp = reinterpret_cast<const uint2*>(rw);
+            uint32_t u[NW];
+            int lu, lw;
+            if (have_lens) {
+                // only the target relator is touched: (NW+1)/2 64-bit loads starting at its
+                // 8-byte aligned base (one word early when NW is odd and the target is r1)
+                constexpr int LD = (NW + 1) / 2;
+                uint32_t t[2 * LD];
+                const uint2* rp = reinterpret_cast<const uint2*>(rw) + (tgt1 ? NW / 2 : 0);
 #pragma unroll
-            for (int j = 0; j < NW; ++j) {  // 64-bit loads of the whole row: fewest LDS wavefronts
-                const uint2 v = rp[j];
-                const int a = 2 * j, b = 2 * j + 1;
-                if (a < NW) w0[a] = v.x; else w1[a - NW] = v.x;
-                if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
-            }
+                for (int j = 0; j < LD; ++j) {
+                    const uint2 v = rp[j];
+                    t[2 * j] = v.x;
+                    t[2 * j + 1] = v.y;
+                }
+                const bool skew = (NW & 1) && tgt1;
 #pragma unroll
-            for (int j = 0; j < NW; ++j) {
-                u[j] = tgt1 ? w1[j] : w0[j];
-                w[j] = tgt1 ? w0[j] : w1[j];
+                for (int j = 0; j < NW; ++j) u[j] = skew ? t[j + 1] : t[j];
+                const int l01 = s_lens[r];
+                lu = tgt1 ? (l01 >> 8) : (l01 & 0xFF);
+                lw = tgt1 ? (l01 & 0xFF) : (l01 >> 8);
+            } else {
+                uint32_t w0[NW], w1[NW], w[NW];
+                const uint2* rp = reinterpret_cast<const uint2*>(rw);
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {  // 64-bit loads of the whole row: fewest LDS wavefronts
+                    const uint2 v = rp[j];
+                    const int a = 2 * j, b = 2 * j + 1;
+                    if (a < NW) w0[a] = v.x; else w1[a - NW] = v.x;
+                    if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
+                }
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {
+                    u[j] = tgt1 ? w1[j] : w0[j];
+                    w[j] = tgt1 ? w0[j] : w1[j];
+                }
+                lu = count_letters<NW>(u);
+                lw = count_letters<NW>(w);
             }
-            const int lu = count_letters<NW>(u), lw = count_letters<NW>(w);
             len0 = tgt1 ? lw : lu;
             len1 = tgt1 ? lu : lw;
             if (lu == 0) status = ST_INDEX;       // relator_nonzero[0] on an empty array
@@ -247,8 +273,17 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
                 if (a < NW) w0[a] = v.x; else w1[a - NW] = v.x;
                 if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
             }
-            Rel<N> r0 = pack_words<NW, N>(w0);
-            Rel<N> r1 = pack_words<NW, N>(w1);
+            Rel<N> r0, r1;
+            if (have_lens) {
+                r0 = pack_words<NW, N, false>(w0);
+                r1 = pack_words<NW, N, false>(w1);
+                const int l01 = s_lens[r];
+                r0.len = l01 & 0xFF;
+                r1.len = l01 >> 8;
+            } else {
+                r0 = pack_words<NW, N>(w0);
+                r1 = pack_words<NW, N>(w1);
+            }
             if (act > 11) {
                 status = ST_ASSERT;  // ac_moves.py:188-190
             } else {

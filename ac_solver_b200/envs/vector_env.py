@@ -25,6 +25,28 @@ from .spaces import Box, Discrete
 from .utils import is_array_valid_presentation
 
 
+def _lens_of(states):
+    """[n, 2*mrl] int8 -> uint8 [n, 2] relator lengths."""
+    m = states.shape[1] // 2
+    return np.stack([np.count_nonzero(states[:, :m], axis=1), np.count_nonzero(states[:, m:], axis=1)],
+                    axis=1).astype(np.uint8)
+
+
+def _normal_form_mask(states):
+    """True for rows whose two words are freely AND cyclically reduced (what ACMove with
+    cyclical=True leaves behind, and what ACS_FLAG_NORMALIZED promises)."""
+    m = states.shape[1] // 2
+    ok = np.ones(len(states), dtype=bool)
+    rows = np.arange(len(states))
+    for h in (states[:, :m].astype(np.int16), states[:, m:].astype(np.int16)):
+        ln = np.count_nonzero(h, axis=1)
+        if m > 1:
+            ok &= ~(((h[:, :-1] + h[:, 1:]) == 0) & (h[:, :-1] != 0)).any(axis=1)
+        last = h[rows, np.maximum(ln - 1, 0)]
+        ok &= ~((ln >= 2) & (h[:, 0] == -last))
+    return ok
+
+
 class _EnvProxy:
     """``envs.envs[i]``: the two things the PPO loop touches (training.py:224,233)."""
 
@@ -87,10 +109,14 @@ class ACVectorEnv:
         self.truncated = torch.zeros(n, dtype=torch.uint8, device=self.dev)
         self.action_log = torch.zeros((n, max(self.horizon_length, 1)), dtype=torch.uint8, device=self.dev)
         self.err = torch.tensor([0, -1], dtype=torch.int64, device=self.dev)
+        self.initial_normal_host = _normal_form_mask(self.initial_states_host)
+        self.initial_lens = torch.from_numpy(_lens_of(self.initial_states_host)).to(self.dev)
+        self.lens = self.initial_lens.clone()  # ACEnv.lengths (ac_env.py:84-92), kernel-maintained
         self._rows = torch.arange(n, device=self.dev)
-        # caller-supplied states may be non-reduced: the first step after a (re)set runs the general
-        # kernel variant; states produced by the kernel are normal forms (ACS_FLAG_NORMALIZED).
-        self._normalized = False
+        # caller-supplied states may be non-reduced: a step after planting such a state runs the
+        # general kernel variant; states produced by the kernel are normal forms, and so are most
+        # datasets (ACS_FLAG_NORMALIZED | ACS_FLAG_LENS_VALID is the steady state).
+        self._normalized = bool(self.initial_normal_host.all())
         self.envs = [_EnvProxy(self, i) for i in range(n)]
 
     # ---------------------------------------------------------------------------------------
@@ -104,13 +130,19 @@ class ACVectorEnv:
         idx = t.as_tensor(np.asarray(indices, dtype=np.int64), device=self.dev)
         self.state[idx] = t.from_numpy(s).to(self.dev)
         self.step_count[idx] = 0
-        self._normalized = False
+        # normal forms keep the steady-state kernel variant valid; anything else forces one
+        # general step (which re-simplifies and recounts every row)
+        if _normal_form_mask(s).all():
+            self.lens[idx] = t.from_numpy(_lens_of(s)).to(self.dev)
+        else:
+            self._normalized = False
 
     def reset(self, *, seed=None, options=None):
         """All environments back to their initial states -> (obs, {})."""
         self.state.copy_(self.initial_states)
         self.step_count.zero_()
-        self._normalized = False
+        self.lens.copy_(self.initial_lens)
+        self._normalized = bool(self.initial_normal_host.all())
         return self.state.cpu().numpy(), {}
 
     def step(self, actions):
@@ -124,11 +156,12 @@ class ACVectorEnv:
         pos = self.step_count.to(t.int64).clamp_(max=self.action_log.shape[1] - 1)
         self.action_log[self._rows, pos] = act
         self.err[0], self.err[1] = 0, -1
-        flags = _lib.FLAG_NORMALIZED if self._normalized else 0
+        # steady state: states are normal forms and self.lens is current (written by the last step)
+        flags = (_lib.FLAG_NORMALIZED | _lib.FLAG_LENS_VALID) if self._normalized else 0
         stream = t.cuda.current_stream(self.dev).cuda_stream
         _lib.check(self.L.acs_env_step_batch(
             self.state.data_ptr(), act.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
-            self.truncated.data_ptr(), self.step_count.data_ptr(), None, None, self.err.data_ptr(),
+            self.truncated.data_ptr(), self.step_count.data_ptr(), self.lens.data_ptr(), None, self.err.data_ptr(),
             self.num_envs, self.max_relator_length, self.horizon_length, flags, stream))
         self._normalized = True
         finished = (self.done | self.truncated).bool()
@@ -150,7 +183,8 @@ class ACVectorEnv:
             fo = np.full(self.num_envs, None, dtype=object)
             fi = np.full(self.num_envs, None, dtype=object)
             mask = np.zeros(self.num_envs, dtype=bool)
-            for k, i in enumerate(fin_idx.cpu().numpy()):
+            fin_host = fin_idx.cpu().numpy()
+            for k, i in enumerate(fin_host):
                 fo[i] = final_obs[k]
                 fi[i] = {"actions": [int(a) for a in logs[k, : lens[k]]]} if solved[k] else {}
                 mask[i] = True
@@ -158,7 +192,9 @@ class ACVectorEnv:
             # auto-reset: the env's own initial state, counters zeroed (gymnasium SyncVectorEnv)
             self.state[fin_idx] = self.initial_states[fin_idx]
             self.step_count[fin_idx] = 0
-            self._normalized = False
+            self.lens[fin_idx] = self.initial_lens[fin_idx]
+            if not self.initial_normal_host[fin_host].all():
+                self._normalized = False  # a non-normal initial state: next step re-simplifies
         if as_numpy:
             return (obs.cpu().numpy(), reward.cpu().numpy(), self.done.cpu().numpy().astype(bool),
                     self.truncated.cpu().numpy().astype(bool), infos)

@@ -30,8 +30,9 @@ sys.path.insert(0, ROOT)
 HORIZON = 200
 # The synthetic states are freely and cyclically reduced, and ACEnv.step keeps them so: the
 # steady-state (ACS_FLAG_NORMALIZED) variant of the kernel is the one an environment runs on
-# every step but the first after a reset with caller-supplied states.
-FLAGS = 2
+# every step but the first after a reset with caller-supplied states.  Like ACEnv.lengths, the
+# relator lengths travel with the state (ACS_FLAG_LENS_VALID).  BENCH_FLAGS=0 times the general variant.
+FLAGS = int(os.environ.get("BENCH_FLAGS", "6"))
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -205,6 +206,9 @@ def run_b200(args):
     done = torch.zeros(rows, dtype=torch.uint8, device="cuda")
     trunc = torch.zeros(rows, dtype=torch.uint8, device="cuda")
     stepc = [torch.zeros(rows, dtype=torch.int32, device="cuda") for _ in range(nbuf)]
+    # ACEnv keeps `lengths` beside `state` (ac_env.py:84-92): so does the batched env (2 B per row)
+    lens = [torch.stack([(s[:, :mrl] != 0).sum(1), (s[:, mrl:] != 0).sum(1)], dim=1).to(torch.uint8).contiguous()
+            for s in states]
     err = torch.tensor([0, -1], dtype=torch.int64, device="cuda")
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
@@ -212,8 +216,8 @@ def run_b200(args):
     def step(i):
         b = i % nbuf
         rc = L.acs_env_step_batch(states[b].data_ptr(), actions[(i // nbuf + b) % nbuf].data_ptr(), reward.data_ptr(),
-                                  done.data_ptr(), trunc.data_ptr(), stepc[b].data_ptr(), None, None, err.data_ptr(),
-                                  rows, mrl, HORIZON, FLAGS, sptr)
+                                  done.data_ptr(), trunc.data_ptr(), stepc[b].data_ptr(), lens[b].data_ptr(), None,
+                                  err.data_ptr(), rows, mrl, HORIZON, FLAGS, sptr)
         if rc != 0:
             _lib.check(rc)
 

@@ -74,6 +74,11 @@ void acs_ctx_destroy(acs_ctx *ctx);
  * with the same flag -- which lets the kernel skip re-validating the untouched relator. */
 #define ACS_FLAG_CYCLICAL 1
 #define ACS_FLAG_NORMALIZED 2
+/* ACS_FLAG_LENS_VALID (only with ACS_FLAG_NORMALIZED and a non-NULL lens array): lens[n,2] holds
+ * the current relator lengths ON ENTRY, exactly as ACEnv keeps `self.lengths` beside `self.state`
+ * (envs/ac_env.py:84-92); the kernel then reads them instead of recounting the letters and
+ * writes the new lengths back.  lens written by a previous call on the same states qualify. */
+#define ACS_FLAG_LENS_VALID 4
 int acs_moves_batch(const int8_t *d_in, const uint8_t *d_action, int8_t *d_out, uint8_t *d_lens,
                     uint8_t *d_status, uint64_t *d_err, int64_t n, int mrl, int flags, void *stream);
 int acs_moves_batch_host(acs_ctx *ctx, const int8_t *h_in, const uint8_t *h_action, int8_t *h_out,

@@ -193,6 +193,45 @@ def test_env_step_batch_vs_oracle():
         assert np.array_equal(d_sc.cpu().numpy(), ref_sc)
 
 
+@pytest.mark.parametrize("mrl", [36, 24, 20])
+def test_env_step_lens_carry(mrl):
+    """Device-pointer env step with the lengths carried beside the state
+    (ACS_FLAG_NORMALIZED | ACS_FLAG_LENS_VALID), chained for 40 steps, vs the oracle."""
+    import torch
+    from ac_solver_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(100 + mrl)
+    n, H = 70_001, 33
+    S = random_rows(rng, n, mrl)
+    S[: n // 3] = random_rows(rng, n // 3, mrl, min_len=mrl - 2)
+    ref_state, ref_sc = S.copy(), np.zeros(n, np.int32)
+    d_state = torch.from_numpy(S.copy()).cuda()
+    d_sc = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_rew = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_done = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_tr = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_lens = torch.from_numpy(np.stack([np.count_nonzero(S[:, :mrl], axis=1), np.count_nonzero(S[:, mrl:], axis=1)],
+                                       axis=1).astype(np.uint8)).cuda()
+    err = torch.tensor([0, -1], dtype=torch.int64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for step in range(40):
+        A = rng.integers(0, 12, size=n).astype(np.uint8)
+        d_a = torch.from_numpy(A).cuda()
+        _lib.check(L.acs_env_step_batch(d_state.data_ptr(), d_a.data_ptr(), d_rew.data_ptr(), d_done.data_ptr(),
+                                        d_tr.data_ptr(), d_sc.data_ptr(), d_lens.data_ptr(), None, err.data_ptr(),
+                                        n, mrl, H, _lib.FLAG_NORMALIZED | _lib.FLAG_LENS_VALID, stream))
+        er, ed, et, el, es = O.env_step_batch(ref_state, A, ref_sc, H)
+        ok = es == 0
+        assert int(err[0]) == int((~ok).sum())
+        err[0] = 0
+        assert np.array_equal(d_state.cpu().numpy(), ref_state)
+        assert np.array_equal(d_lens.cpu().numpy()[ok], el[ok])
+        assert np.array_equal(d_rew.cpu().numpy()[ok], er[ok])
+        assert np.array_equal(d_done.cpu().numpy()[ok], ed[ok]) and np.array_equal(d_tr.cpu().numpy()[ok], et[ok])
+        assert np.array_equal(d_sc.cpu().numpy(), ref_sc)
+
+
 def test_env_traces_golden(env_traces):
     """ACEnv (single env, reference API) reproduces the reference's trajectories."""
     from ac_solver_b200 import ACEnv, ACEnvConfig
