@@ -150,7 +150,7 @@ __device__ __forceinline__ void store_relator(uint32_t* wp, const Rel<N>& t) {
 // of uniformly random moves never enter the packed domain.  Per-row results are staged in
 // shared memory and written back by the thread that owns the row index, so every global
 // access stays coalesced.
-template <int NW, bool TRUSTED, int TR>
+template <int NW, bool TRUSTED, bool LENS, int TR>
 __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(const StepParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -178,11 +178,11 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
     const bool active = tid < nrows;
     int action = 255;
     int sc = 0;
-    const bool have_lens = TRUSTED && P.lens_valid;  // lengths carried beside the state (ac_env.py:84-92)
+    constexpr bool have_lens = TRUSTED && LENS;  // lengths carried beside the state (ac_env.py:84-92)
     if (active) {
         action = P.action[row];
         if (P.reward) sc = P.step_count[row];
-        if (have_lens) s_lens[tid] = reinterpret_cast<const uint16_t*>(P.lens)[row];
+        if constexpr (have_lens) s_lens[tid] = reinterpret_cast<const uint16_t*>(P.lens)[row];
     }
     const bool is_concat = active && !(action >= 4 && action <= 11);
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, is_concat);
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
             const bool tgt1 = ((act + 1) & 1) != 0;
             uint32_t u[NW];
             int lu, lw;
-            if (have_lens) {
+            if constexpr (have_lens) {
                 // only the target relator is touched: (NW+1)/2 64-bit loads starting at its
                 // 8-byte aligned base (one word early when NW is odd and the target is r1)
                 constexpr int LD = (NW + 1) / 2;
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
                 if (b < NW) w0[b] = v.y; else w1[b - NW] = v.y;
             }
             Rel<N> r0, r1;
-            if (have_lens) {
+            if constexpr (have_lens) {
                 r0 = pack_words<NW, N, false>(w0);
                 r1 = pack_words<NW, N, false>(w1);
                 const int l01 = s_lens[r];
@@ -389,8 +389,9 @@ static cudaError_t launch_words(const StepParams& P, cudaStream_t s) {
         constexpr int TR = decltype(tr)::value;
         const int64_t tiles = (P.n + TR - 1) / TR;
         const size_t smem = (size_t)TR * 8 * NW;
-        if (P.trusted) ac_step_words_kernel<NW, true, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
-        else ac_step_words_kernel<NW, false, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
+        if (P.trusted && P.lens_valid) ac_step_words_kernel<NW, true, true, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
+        else if (P.trusted) ac_step_words_kernel<NW, true, false, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
+        else ac_step_words_kernel<NW, false, false, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
     };
     if constexpr (NW == 9) {
         if (tile_rows == 64) launch(std::integral_constant<int, 64>{});
