@@ -72,6 +72,8 @@ _SIGS = {
     "acs_env_step_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P]),
     "acs_env_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int,
                                     C.POINTER(C.c_int64)]),
+    "acs_vecenv_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int,
+                                  C.c_int, C.c_int, _P]),
     "acs_validate_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "acs_validate_batch_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "acs_generic_batch": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -25,6 +25,8 @@ struct StepParams {
     int bulk_ok;            // in/out are 16-byte aligned: TMA bulk copies allowed
     int trusted;            // rows are normal forms for `cyclical` (see ac_core.cuh apply_move)
     int lens_valid;         // `lens` holds the current relator lengths on entry (in/out)
+    uint8_t* action_log;    // [n, log_stride] or null: action written at the pre-step counter (env only)
+    int log_stride;
 };
 
 // thread-local error text behind acs_last_error() (capi.cu)
@@ -55,5 +57,8 @@ struct GenericParams {
 };
 cudaError_t launch_generic(const GenericParams& P, cudaStream_t s);
 cudaError_t launch_validate(const int8_t* in, uint8_t* flags, int64_t n, int mrl, cudaStream_t s);
+cudaError_t launch_autoreset(int8_t* state, const int8_t* init, int8_t* final_obs, const uint8_t* done,
+                             const uint8_t* trunc, int32_t* step_count, int32_t* final_steps, uint8_t* lens,
+                             const uint8_t* init_lens, int64_t n, int mrl, cudaStream_t s);
 
 }  // namespace acs

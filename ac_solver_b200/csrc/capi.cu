@@ -165,6 +165,44 @@ int acs_env_step_batch(int8_t* d_state, const uint8_t* d_action, int32_t* d_rewa
     return ACS_OK;
 }
 
+int acs_vecenv_step(int8_t* d_state, const int8_t* d_initial_state, const uint8_t* d_action, int32_t* d_reward,
+                    uint8_t* d_done, uint8_t* d_truncated, int32_t* d_step_count, uint8_t* d_lens,
+                    const uint8_t* d_initial_lens, uint8_t* d_action_log, int log_stride, int8_t* d_final_obs,
+                    int32_t* d_final_steps, uint64_t* d_err, int64_t n, int mrl, int horizon, int flags, void* stream) {
+    if (n < 0 || (n > 0 && (!d_state || !d_initial_state || !d_action || !d_reward || !d_done || !d_truncated ||
+                            !d_step_count)))
+        return fail(ACS_ERR_INVALID, "null buffer");
+    if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
+    if (d_action_log && (mrl % 4 != 0 || log_stride < 1))
+        return fail(ACS_ERR_UNSUPPORTED, "the action log needs max_relator_length % 4 == 0 and log_stride >= 1");
+    if (d_lens && !d_initial_lens) return fail(ACS_ERR_INVALID, "d_lens needs d_initial_lens for the auto-reset");
+    acs::StepParams P{};
+    P.in = d_state;
+    P.out = d_state;
+    P.action = d_action;
+    P.lens = d_lens;
+    P.err = reinterpret_cast<unsigned long long*>(d_err);
+    P.reward = d_reward;
+    P.done = d_done;
+    P.truncated = d_truncated;
+    P.step_count = d_step_count;
+    P.n = n;
+    P.mrl = mrl;
+    P.cyclical = 1;
+    P.trusted = (flags & ACS_FLAG_NORMALIZED) ? 1 : 0;
+    P.lens_valid = ((flags & ACS_FLAG_LENS_VALID) && P.trusted && d_lens) ? 1 : 0;
+    P.horizon = horizon;
+    P.max_reward = horizon * mrl * 2;
+    P.bulk_ok = aligned16(d_state);
+    P.action_log = d_action_log;
+    P.log_stride = log_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ACS_CUDA(acs::launch_step(P, s));
+    ACS_CUDA(acs::launch_autoreset(d_state, d_initial_state, d_final_obs, d_done, d_truncated, d_step_count,
+                                   d_final_steps, d_lens, d_initial_lens, n, mrl, s));
+    return ACS_OK;
+}
+
 int acs_validate_batch(const int8_t* d_in, uint8_t* d_flags, int64_t n, int mrl, void* stream) {
     if (n < 0 || (n > 0 && (!d_in || !d_flags)) || mrl < 1) return fail(ACS_ERR_INVALID, "bad argument");
     ACS_CUDA(acs::launch_validate(d_in, d_flags, n, mrl, static_cast<cudaStream_t>(stream)));

@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
                 P.done[row] = (uint8_t)d;
                 P.step_count[row] = sc + 1;
                 P.truncated[row] = (uint8_t)(sc + 1 >= P.horizon);
+                if (P.action_log)  // ACEnv.actions (ac_env.py:96): the episode's move sequence
+                    P.action_log[row * P.log_stride + min(sc, P.log_stride - 1)] = (uint8_t)action;
             }
         }
     }
@@ -432,6 +434,39 @@ cudaError_t launch_step(const StepParams& P, cudaStream_t s) {
         case 3: return launch_bytes<3>(P, s);
         default: return launch_bytes<4>(P, s);
     }
+}
+
+// Auto-reset of finished environments (gymnasium 0.28.1 SyncVectorEnv semantics, see
+// envs/vector_env.py): rows with done|truncated hand their last observation to final_obs and go
+// back to their own initial state with zeroed counters.  One thread per 2 bytes of a row.
+__global__ void __launch_bounds__(256) env_autoreset_kernel(uint16_t* state, const uint16_t* init, uint16_t* final_obs,
+                                                            const uint8_t* done, const uint8_t* trunc,
+                                                            int32_t* step_count, int32_t* final_steps,
+                                                            uint16_t* lens, const uint16_t* init_lens, int64_t n,
+                                                            int mrl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * mrl) return;
+    const int64_t row = i / mrl;
+    if (!(done[row] | trunc[row])) return;
+    if (final_obs) final_obs[i] = state[i];
+    state[i] = init[i];
+    if (i % mrl == 0) {
+        if (final_steps) final_steps[row] = step_count[row];
+        step_count[row] = 0;
+        if (lens) lens[row] = init_lens[row];
+    }
+}
+
+cudaError_t launch_autoreset(int8_t* state, const int8_t* init, int8_t* final_obs, const uint8_t* done,
+                             const uint8_t* trunc, int32_t* step_count, int32_t* final_steps, uint8_t* lens,
+                             const uint8_t* init_lens, int64_t n, int mrl, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t total = n * mrl;
+    env_autoreset_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        reinterpret_cast<uint16_t*>(state), reinterpret_cast<const uint16_t*>(init),
+        reinterpret_cast<uint16_t*>(final_obs), done, trunc, step_count, final_steps, reinterpret_cast<uint16_t*>(lens),
+        reinterpret_cast<const uint16_t*>(init_lens), n, mrl);
+    return cudaGetLastError();
 }
 
 }  // namespace acs

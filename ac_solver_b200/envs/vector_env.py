@@ -117,6 +117,9 @@ class ACVectorEnv:
         # general kernel variant; states produced by the kernel are normal forms, and so are most
         # datasets (ACS_FLAG_NORMALIZED | ACS_FLAG_LENS_VALID is the steady state).
         self._normalized = bool(self.initial_normal_host.all())
+        self._fast_ok = self._normalized and self.max_relator_length % 4 == 0
+        self.final_obs = torch.zeros_like(self.state)
+        self.final_steps = torch.zeros(n, dtype=torch.int32, device=self.dev)
         self.envs = [_EnvProxy(self, i) for i in range(n)]
 
     # ---------------------------------------------------------------------------------------
@@ -199,6 +202,47 @@ class ACVectorEnv:
             return (obs.cpu().numpy(), reward.cpu().numpy(), self.done.cpu().numpy().astype(bool),
                     self.truncated.cpu().numpy().astype(bool), infos)
         return obs.clone(), reward, self.done.bool(), self.truncated.bool(), infos
+
+    # ---------------------------------------------------------------------------------------
+    def step_device(self, actions):
+        """GPU-resident step without any host synchronisation (CUDA-graph capturable): one
+        ``acs_vecenv_step`` call = fused env-step kernel + auto-reset kernel.
+
+        actions: CUDA tensor (any integer dtype).  Returns live views ``(obs int8 [N, 2*mrl],
+        reward int32 [N], done uint8 [N], truncated uint8 [N])`` that the next call overwrites.
+        Finished environments are already reset in ``obs``; their last observation is in
+        ``self.final_obs``, the episode length in ``self.final_steps`` and -- for solved ones --
+        the move sequence via ``final_actions(i)``.  Reward clipping (if configured) is applied by
+        ``clipped_reward()``.  Errors (a move emptying a relator) accumulate in ``self.err`` and
+        are raised by ``check_errors()``."""
+        t = self.torch
+        if not (self._fast_ok and self._normalized):
+            raise _lib.AcsError("step_device needs normal-form states (initial and planted) and "
+                                "max_relator_length % 4 == 0; use step()")
+        act = actions if actions.dtype == t.uint8 else actions.to(t.uint8)
+        _lib.check(self.L.acs_vecenv_step(
+            self.state.data_ptr(), self.initial_states.data_ptr(), act.data_ptr(), self.reward.data_ptr(),
+            self.done.data_ptr(), self.truncated.data_ptr(), self.step_count.data_ptr(), self.lens.data_ptr(),
+            self.initial_lens.data_ptr(), self.action_log.data_ptr(), self.action_log.shape[1],
+            self.final_obs.data_ptr(), self.final_steps.data_ptr(), self.err.data_ptr(), self.num_envs,
+            self.max_relator_length, self.horizon_length, _lib.FLAG_NORMALIZED | _lib.FLAG_LENS_VALID,
+            t.cuda.current_stream(self.dev).cuda_stream))
+        return self.state, self.reward, self.done, self.truncated
+
+    def clipped_reward(self):
+        r = self.reward.to(self.torch.float32)
+        return r if self.clip_rewards is None else r.clamp(self.clip_rewards[0], self.clip_rewards[1])
+
+    def final_actions(self, i):
+        """``info["actions"]`` of the episode environment i finished in the last ``step_device``."""
+        n = int(self.final_steps[i])
+        return [int(a) for a in self.action_log[i, :n].cpu().numpy()]
+
+    def check_errors(self):
+        n_bad = int(self.err[0])
+        if n_bad:
+            raise AssertionError(f"{n_bad} environment steps produced an invalid presentation (first: env "
+                                 f"{int(self.err[1])}); the reference raises AssertionError (envs/utils.py:261-263)")
 
     def close(self):
         pass

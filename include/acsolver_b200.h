@@ -101,6 +101,19 @@ int acs_env_step_host(acs_ctx *ctx, int8_t *d_state, int32_t *d_step_count, cons
                       int8_t *h_obs, int32_t *h_reward, uint8_t *h_done, uint8_t *h_truncated,
                       int64_t n, int mrl, int horizon, int flags, int64_t *n_bad);
 
+/* Vector-environment step for GPU-resident rollouts: acs_env_step_batch followed, in the same
+ * stream and with no host involvement, by the auto-reset of gymnasium's SyncVectorEnv as the
+ * reference uses it (agents/environment.py:60-127): environments with done|truncated copy their
+ * observation to d_final_obs and their episode length to d_final_steps (either may be NULL) and
+ * return to d_initial_state with zeroed counters.
+ * d_action_log [n, log_stride] (may be NULL) receives each action at the pre-step counter, i.e.
+ * ACEnv.actions (envs/ac_env.py:96).  Capturable in a CUDA graph (no allocation, no sync). */
+int acs_vecenv_step(int8_t *d_state, const int8_t *d_initial_state, const uint8_t *d_action, int32_t *d_reward,
+                    uint8_t *d_done, uint8_t *d_truncated, int32_t *d_step_count, uint8_t *d_lens,
+                    const uint8_t *d_initial_lens, uint8_t *d_action_log, int log_stride, int8_t *d_final_obs,
+                    int32_t *d_final_steps, uint64_t *d_err, int64_t n, int mrl, int horizon, int flags,
+                    void *stream);
+
 /* ---- boundary validation (envs/utils.py:13-54) ------------------------------------ */
 /* flags[row]: bit0 is_array_valid_presentation, bit1 letters in {0,+-1,+-2},
  * bit2 zeros only on the right of each half. */

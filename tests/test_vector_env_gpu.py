@@ -70,6 +70,47 @@ def test_vector_env_matches_looped_oracle(miller_schupp, numpy_io):
     assert n_done > 0 and n_trunc > 0
 
 
+def test_step_device_matches_looped_oracle(miller_schupp):
+    """The sync-free path (fused step + auto-reset kernels, lengths carried, action log on the
+    device) against the same per-environment oracle loop."""
+    import torch
+    from ac_solver_b200.envs.vector_env import ACVectorEnv
+
+    n, H = 300, 13
+    init = _initial_states(miller_schupp, n)
+    env = ACVectorEnv(init, horizon_length=H)
+    env.reset()
+    ref_state, ref_sc = init.copy(), np.zeros(n, np.int32)
+    ref_log = [[] for _ in range(n)]
+    rng = np.random.default_rng(9)
+    n_done = 0
+    for step in range(70):
+        A = rng.integers(0, 12, size=n).astype(np.uint8)
+        A[:6] = rng.choice([0, 1, 2, 3], size=6)
+        obs, rew, done, trunc = env.step_device(torch.from_numpy(A).cuda())
+        for i in range(n):
+            ref_log[i].append(int(A[i]))
+        er, ed, et, el, es = O.env_step_batch(ref_state, A, ref_sc, H)
+        assert not es.any()
+        fin = ed.astype(bool) | et.astype(bool)
+        final_obs = env.final_obs.cpu().numpy()
+        final_steps = env.final_steps.cpu().numpy()
+        for i in np.flatnonzero(fin):
+            assert np.array_equal(final_obs[i], ref_state[i])
+            assert final_steps[i] == len(ref_log[i])
+            if ed[i]:
+                assert env.final_actions(i) == ref_log[i]
+                n_done += 1
+            ref_state[i], ref_sc[i], ref_log[i] = init[i], 0, []
+        assert np.array_equal(obs.cpu().numpy(), ref_state)
+        assert np.array_equal(rew.cpu().numpy(), er)
+        assert np.array_equal(done.cpu().numpy(), ed) and np.array_equal(trunc.cpu().numpy(), et)
+        assert np.array_equal(env.step_count.cpu().numpy(), ref_sc)
+        assert np.array_equal(env.lens.cpu().numpy()[:, 0], np.count_nonzero(ref_state[:, :36], axis=1))
+    env.check_errors()
+    assert n_done > 0
+
+
 def test_vector_env_errors(miller_schupp):
     from ac_solver_b200.envs.vector_env import ACVectorEnv
 
