@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1 << 17)
     ap.add_argument("--skip-bfs", action="store_true")
     ap.add_argument("--bfs-budget", type=int, default=100_000_000)
+    ap.add_argument("--bfs-timeout", type=float, default=90.0)
     return ap.parse_args()
 
 
@@ -182,6 +183,10 @@ def run_b200(args):
     rank, local_rank, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the AC-move kernels have no CPU fallback")
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version
+    # banner there) are sent to stderr until the line is printed.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
@@ -280,20 +285,14 @@ def run_b200(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
-    bfs_line = None
-    if not args.skip_bfs and (rank == 0 or world > 1):
-        try:
-            bfs_line = bench_bfs(args, world, dist)
-        except Exception as e:  # the search bench is auxiliary; never lose the headline line
-            bfs_line = {"error": repr(e)}
-
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         ms_per_step = ms / args.steps
         moves_per_s = world * rows * args.steps / (ms * 1e-3)
         algo_bytes = 4 * mrl + 6  # 2*mrl in + 2*mrl out + action 1 + reward 4 + done 1 (150 at mrl 36)
         achieved = algo_bytes * rows / (ms_per_step * 1e-3) / 1e9
-        cpu = cpu_baseline(args.cpu_sample_rows, mrl)
+        # the CPU baseline is timed on rank 0 at N=1 only (it would stall the other ranks)
+        cpu = cpu_baseline(args.cpu_sample_rows, mrl) if world == 1 else None
         line = {
             "metric": "AC moves/sec (batched env steps)",
             "value": moves_per_s,
@@ -334,9 +333,38 @@ def run_b200(args):
             "gpu_launches": args.steps,
             "clocks": sampler.summary(),
         }
-        if bfs_line is not None:
-            line["bfs"] = bfs_line
-        print(json.dumps(line), flush=True)
+    else:
+        line = None
+
+    def emit(extra=None):
+        if rank == 0:
+            if extra is not None:
+                line["bfs"] = extra
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+            print(json.dumps(line), flush=True)
+
+    # Secondary metric (BFS nodes expanded/s).  At N > 1 it is a multi-rank collective program: a
+    # watchdog guarantees that the headline line is printed and every rank exits even if it stalls.
+    bfs_line = None
+    if not args.skip_bfs and (rank == 0 or world > 1):
+        def bail():
+            emit({"error": f"sharded bfs did not finish within {args.bfs_timeout} s"})
+            os._exit(0)
+
+        dog = threading.Timer(args.bfs_timeout, bail)
+        dog.daemon = True
+        dog.start()
+        try:
+            bfs_line = bench_bfs(args, world, dist)
+        except Exception as e:  # the search bench is auxiliary; never lose the headline line
+            bfs_line = {"error": repr(e)}
+            if world > 1:  # ranks may be out of step now: no further collectives
+                dog.cancel()
+                emit(bfs_line)
+                os._exit(0)
+        dog.cancel()
+    emit(bfs_line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -39,8 +39,9 @@ def _worker(rank, world, port, q):
     q.put((rank, out))
 
 
-@pytest.mark.timeout(600)
-def test_sharded_bfs_world2_gloo():
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_bfs_gloo(world):
     from oracle import oracle as O
 
     s = socket.socket()
@@ -49,10 +50,10 @@ def test_sharded_bfs_world2_gloo():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = dict(q.get(timeout=500) for _ in procs)
+    results = dict(q.get(timeout=800) for _ in procs)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -60,13 +61,13 @@ def test_sharded_bfs_world2_gloo():
         try:
             es, ep, ei = O.bfs(np.array(pres, np.int8), budget, cyc, want_visited=True)
         except AssertionError:
-            assert results[0][k] == "AssertionError" and results[1][k] == "AssertionError"
+            assert all(results[r][k] == "AssertionError" for r in range(world))
             continue
-        for rank in (0, 1):
+        for rank in range(world):
             solved, path, nv, ne, bh, mins, vis, nloc = results[rank][k]
             assert (solved, path) == (es, ep), (k, rank)
             assert (nv, ne, bh, mins) == (ei["n_visited"], ei["n_expanded"], ei["budget_hit"], ei["minlen_log"]), (k, rank)
         assert np.array_equal(results[0][k][6], ei["visited"]), k  # rank 0 holds the gathered, ordered array
         if ei["n_visited"] > 100:  # both shards actually hold nodes
-            assert results[0][k][7] > 0 and results[1][k][7] > 0
-            assert results[0][k][7] + results[1][k][7] == ei["n_visited"]
+            assert all(results[r][k][7] > 0 for r in range(world))
+            assert sum(results[r][k][7] for r in range(world)) == ei["n_visited"]
