@@ -38,8 +38,12 @@ constexpr uint64_t kTentBit = 1ull << 63;
 constexpr uint64_t kMask26 = (1ull << 26) - 1;
 constexpr int kMaxWorld = 16;
 
+// The owner must be statistically independent of the table slot (low bits of h) and of the
+// fingerprints (high bits): taking it from a bit range of h itself pins those bits for every key
+// a rank owns, which clusters its table into 1/world of the slots once the table is larger than
+// that bit position (found at 8 GPUs: probe chains exploded for tables >= 2^25 slots).
 __host__ __device__ __forceinline__ int owner_of(uint64_t h, int world) {
-    return (int)((uint32_t)((h >> 22) & 0xFFFFFu) % (uint32_t)world);
+    return (int)((uint32_t)(mix64(h ^ 0x9e3779b97f4a7c15ull) >> 40) % (uint32_t)world);
 }
 
 template <int W>

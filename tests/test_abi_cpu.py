@@ -89,3 +89,23 @@ def test_env_config_errors():
     env = ACEnv(cfg)
     assert env.max_relator_length == 3 and env.max_reward == 7 * 3 * 2 and env.lengths == [2, 1]
     assert env.observation_space.shape == (6,) and env.action_space.n == 12
+
+
+def test_shard_owner_is_independent_of_table_slot():
+    """The owner rank of a key must not pin bits of its table slot (a correlation clustered the
+    per-rank tables at 8 GPUs): for keys of one owner, every 3-bit window of the low 32 hash bits
+    stays uniform."""
+    from ac_solver_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    hs = rng.integers(0, 2**63, size=40000, dtype=np.int64).astype(np.uint64)
+    for world in (2, 3, 8):
+        owners = np.array([L.acs_sbfs_owner(int(h), world) for h in hs])
+        counts = np.bincount(owners, minlength=world)
+        assert counts.min() > 0.8 * len(hs) / world
+        mine = hs[owners == 0]
+        for shift in range(0, 30):
+            win = ((mine >> np.uint64(shift)) & np.uint64(7)).astype(np.int64)
+            c = np.bincount(win, minlength=8)
+            assert c.min() > 0.6 * len(mine) / 8, (world, shift, c)
