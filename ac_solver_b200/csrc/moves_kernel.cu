@@ -166,10 +166,14 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
     const int nrows = (int)min((int64_t)TR, P.n - row0);
     const bool bulk = P.bulk_ok && nrows == TR;
 
+    // PDL: let the next grid of the stream start launching, then wait for the previous grid's
+    // memory before touching global data (no-ops when launched without the attribute)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (bulk && tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     tile_load(smem, &bar, P, row0, nrows, bulk);
 
@@ -391,9 +395,26 @@ static cudaError_t launch_words(const StepParams& P, cudaStream_t s) {
         constexpr int TR = decltype(tr)::value;
         const int64_t tiles = (P.n + TR - 1) / TR;
         const size_t smem = (size_t)TR * 8 * NW;
-        if (P.trusted && P.lens_valid) ac_step_words_kernel<NW, true, true, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
-        else if (P.trusted) ac_step_words_kernel<NW, true, false, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
-        else ac_step_words_kernel<NW, false, false, TR><<<(unsigned)tiles, TR, smem, s>>>(P);
+        // Programmatic dependent launch: the next step kernel in the stream may become resident
+        // while this one drains; it blocks in griddepcontrol.wait before its first global access,
+        // so stream ordering of the data is unchanged (ACS_PDL=0 disables).
+        static const bool pdl = [] {
+            const char* e = getenv("ACS_PDL");
+            return !(e && e[0] == '0');
+        }();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)tiles);
+        cfg.blockDim = dim3(TR);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        if (P.trusted && P.lens_valid) cudaLaunchKernelEx(&cfg, ac_step_words_kernel<NW, true, true, TR>, P);
+        else if (P.trusted) cudaLaunchKernelEx(&cfg, ac_step_words_kernel<NW, true, false, TR>, P);
+        else cudaLaunchKernelEx(&cfg, ac_step_words_kernel<NW, false, false, TR>, P);
     };
     if constexpr (NW == 9) {
         if (tile_rows == 64) launch(std::integral_constant<int, 64>{});
