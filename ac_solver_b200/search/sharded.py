@@ -157,8 +157,9 @@ class GpuShardOps:
         self.l0, self.l1 = int(lo_hi[0]), int(lo_hi[1])
         self.nwords = (12 * self.F + 31) // 32
         self.bitmap_local = t.zeros(self.nwords, dtype=t.int32, device=self.dev)
-        self.prefix_local = t.empty(self.nwords + 1, dtype=t.int32, device=self.dev)
-        self.prefix_global = t.empty(self.nwords + 1, dtype=t.int32, device=self.dev)
+        nscr = self.nwords + 2 + (self.nwords + 2047) // 2048  # prefixes + total + scan scratch
+        self.prefix_local = t.empty(nscr, dtype=t.int32, device=self.dev)
+        self.prefix_global = t.empty(nscr, dtype=t.int32, device=self.dev)
 
     def _chunk_args(self, **kw):
         return self._fill(l0=self.l0, l1=self.l1, head=self.head, nparents=self.F, n_nodes=self.n_nodes,

@@ -208,6 +208,7 @@ int acs_sbfs_pack_root(const int8_t *h_presentation, int mrl, uint64_t *key_out4
 int acs_sbfs_owner(uint64_t hash, int world);
 int acs_sbfs_expand(const acs_sbfs_args *a, int phase, void *stream);
 int acs_sbfs_insert_mark(const acs_sbfs_args *a, void *stream);
+/* d_prefix: nwords+1 prefixes (the last is the total) followed by ceil(nwords/2048)+1 words of scratch */
 int acs_sbfs_scan(const uint32_t *d_bitmap, uint32_t *d_prefix, int64_t nwords, void *stream);
 int acs_sbfs_cut(const acs_sbfs_args *a, void *stream);
 int acs_sbfs_rank_at(const acs_sbfs_args *a, uint64_t *d_out2, void *stream);
