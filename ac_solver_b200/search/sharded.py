@@ -101,9 +101,19 @@ class GpuShardOps:
         self.ctrl = torch.empty(130, **i64)
         self.small = torch.zeros(8, **i64)
         self.args = _lib.SbfsArgs()
-        self._keep = []
+        self._bufs = {}
 
     # -- helpers --
+    def _buf(self, name, n, dtype, cols=None):
+        """Grow-only scratch tensor reused across chunks (no allocator traffic in the loop)."""
+        n = max(int(n), 1)
+        cur = self._bufs.get(name)
+        if cur is None or cur.shape[0] < n:
+            shape = (int(n * 1.25) + 16,) if cols is None else (int(n * 1.25) + 16, cols)
+            cur = self.torch.empty(shape, dtype=dtype, device=self.dev)
+            self._bufs[name] = cur
+        return cur[:n]
+
     def _stream(self):
         return self.torch.cuda.current_stream(self.dev).cuda_stream
 
@@ -156,10 +166,10 @@ class GpuShardOps:
         lo_hi = self.small[:2].cpu()
         self.l0, self.l1 = int(lo_hi[0]), int(lo_hi[1])
         self.nwords = (12 * self.F + 31) // 32
-        self.bitmap_local = t.zeros(self.nwords, dtype=t.int32, device=self.dev)
+        self.bitmap_local = self._buf("bitmap_local", self.nwords, t.int32).zero_()
         nscr = self.nwords + 2 + (self.nwords + 2047) // 2048  # prefixes + total + scan scratch
-        self.prefix_local = t.empty(nscr, dtype=t.int32, device=self.dev)
-        self.prefix_global = t.empty(nscr, dtype=t.int32, device=self.dev)
+        self.prefix_local = self._buf("prefix_local", nscr, t.int32)
+        self.prefix_global = self._buf("prefix_global", nscr, t.int32)
 
     def _chunk_args(self, **kw):
         return self._fill(l0=self.l0, l1=self.l1, head=self.head, nparents=self.F, n_nodes=self.n_nodes,
@@ -180,8 +190,8 @@ class GpuShardOps:
         n = int(counts.sum())
         offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
         cursor = t.from_numpy(offs).to(self.dev)
-        send_keys = t.empty((max(n, 1), 2 * self.W), dtype=t.int64, device=self.dev)
-        send_c = t.empty(max(n, 1), dtype=t.int32, device=self.dev)
+        send_keys = self._buf("send_keys", n, t.int64, cols=2 * self.W)
+        send_c = self._buf("send_c", n, t.int32)
         _lib.check(self.L.acs_sbfs_expand(self._chunk_args(dest_cursor=cursor.data_ptr(),
                                                            send_keys=send_keys.data_ptr(),
                                                            send_c=send_c.data_ptr()), 1, self._stream()))
@@ -191,9 +201,11 @@ class GpuShardOps:
         t = self.torch
         self.recv_keys, self.recv_c = recv_keys.contiguous(), recv_c.contiguous()
         self.n_recv = int(self.recv_c.shape[0])
-        self.rec_slot = t.empty(max(self.n_recv, 1), dtype=t.int32, device=self.dev)
+        self.rec_slot = self._buf("rec_slot", self.n_recv, t.int32)
         _lib.check(self.L.acs_sbfs_insert_mark(self._recv_args(), self._stream()))
-        return self.bitmap_local.clone()
+        out = self._buf("bitmap_global", self.nwords, t.int32)
+        out.copy_(self.bitmap_local)
+        return out
 
     def _recv_args(self, **kw):
         return self._chunk_args(recv_keys=self.recv_keys.data_ptr(), recv_c=self.recv_c.data_ptr(), n_recv=self.n_recv,
