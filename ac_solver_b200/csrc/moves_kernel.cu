@@ -9,10 +9,16 @@
 //     memory by ONE TMA bulk copy (cp.async.bulk, mbarrier completion) and back by ONE
 //     bulk store, so global traffic is fully coalesced 16-byte bursts although a row is
 //     72 bytes (8-byte aligned only);
-//   * one thread owns one row: 64-bit conflict-free LDS of the row, int8 -> 2-bit codes
-//     with multiply-gathers (ac_pack.cuh), the move on registers (ac_core.cuh), 2-bit ->
-//     int8 with a PRMT table lookup, and only the REWRITTEN relator is stored back;
-//   * reward / done / truncated / step counter are fused into the same pass.
+//   * one thread owns one row; the rows of a tile are re-assigned by move class (ballot +
+//     popc prefix) so that warps are uniform: concatenations go through 2-bit packed
+//     registers (int8 -> codes with multiply-gathers, ac_pack.cuh; the move in ac_core.cuh;
+//     codes -> int8 with a PRMT table lookup), conjugations of normal-form states are a
+//     one-letter rotation done directly on the int8 words; only the REWRITTEN relator is
+//     stored back;
+//   * reward / done / truncated / step counter / lengths / action log are fused into the
+//     same pass, staged in shared memory and written coalesced by the row's owner thread;
+//   * consecutive launches overlap their ramp and drain by programmatic dependent launch.
+// Measured: 27.8 us for 1 Mi rows at mrl 36 = 0.875 of the measured HBM copy peak.
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>

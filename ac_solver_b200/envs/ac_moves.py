@@ -82,6 +82,9 @@ def ac_moves_batch(states, actions, cyclical=True, validate=True, normalized=Fal
         if not ((flags & 6) == 6).all():
             bad = int(np.flatnonzero((flags & 6) != 6)[0])
             raise ValueError(f"row {bad} is not a right-padded word pair over {{+-1,+-2}}")
+    if w // 2 > 64:  # beyond the packed kernels' width: the generic byte kernel (any width <= 127)
+        out, aux, status = generic_call(_lib.OP_ACMOVE, s, actions=a, cyclical=cyclical, device=device)
+        return out, aux.astype(np.uint8), status
     out = np.empty_like(s)
     lens = np.zeros((n, 2), np.uint8)
     status = np.zeros(n, np.uint8)

@@ -77,7 +77,14 @@ def greedy_search(presentation, max_nodes_to_explore=10000, verbose=False, cycli
             print(f"New minimal length found: {m}")
     _raise_for(info["status"])
     if solved:
-        if verbose:  # greedy.py:92-99; the final state's single letters are not tracked on the host
+        if verbose:  # greedy.py:92-99: the three lines of the reference, from a replay of the path
+            from ..envs.ac_moves import ACMove
+
+            state, lens = p.copy(), [0, 0]
+            for action, _ in path[1:]:
+                state, lens = ACMove(action, state, mrl, lens, cyclical=cyclically_reduce_after_moves)
+            print(f"Found {state[0:1], state[mrl:mrl + 1]} after exploring "
+                  f"{info['n_visited'] - info['frontier_left']} nodes")
             print(f"Path to a trivial state: (tuples are of form (action, length of a state)) {path}")
             print(f"Total path length: {len(path)}")
         return True, path

@@ -94,3 +94,29 @@ def test_greedy_wide_keys_and_errors():
         O.greedy_search(q, 100)
     with pytest.raises(AssertionError):
         greedy_search(q, 100)
+
+
+def test_greedy_verbose_stdout(search_cases, capsys):
+    """verbose=True prints the reference's lines (greedy.py:82-99).  The fixture was recorded under
+    numpy 2, which prints lengths as np.int64(11); the reference's pinned numpy 1.24 prints 11."""
+    import re
+    from ac_solver_b200 import greedy_search
+
+    c = [c for c in search_cases["greedy"] if c["solved"] and len(c["presentation"]) == 14 and not c["cyclical"]][0]
+    ok, path = greedy_search(np.array(c["presentation"]), c["budget"], verbose=True)
+    assert ok
+    expected = re.sub(r"np\.int64\((\d+)\)", r"\1", c["stdout"])
+    assert capsys.readouterr().out == expected
+
+
+def test_moves_batch_beyond_packed_width():
+    """max_relator_length > 64 is served by the generic byte kernel."""
+    from ac_solver_b200 import ac_moves_batch
+    from ac_solver_b200.synthetic import random_actions, random_presentations
+
+    S = random_presentations(3000, 100, seed=5)
+    A = random_actions(3000, seed=6)
+    out, lens, status = ac_moves_batch(S, A, cyclical=True)
+    eo, el, es = O.moves_batch(S, A, cyclical=True)
+    assert np.array_equal(status, es) and np.array_equal(out, eo)
+    assert np.array_equal(lens[es == 0], el[es == 0])
