@@ -416,11 +416,20 @@ def bench_bfs(args, world=1, dist=None):
     t0 = time.perf_counter()
     solved, path, info = bfs_device(ak3, args.bfs_budget)
     wall = time.perf_counter() - t0
+    # CPU baseline beside it: the C oracle's sequential bfs on one core,
+    # bounded to a 2e6-node budget of the same search
+    from oracle import oracle as O
+
+    c0 = time.perf_counter()
+    _, _, cinfo = O.bfs(ak3, 2_000_000)
+    cpu_s = time.perf_counter() - c0
     return {
         "metric": "BFS nodes expanded/sec", "workload": f"bfs AK(3) mrl 24 budget {args.bfs_budget}, 1 GPU",
         "nodes_expanded": info["n_expanded"], "visited": info["n_visited"], "levels": info["n_levels"],
         "expanded_per_s_device": info["n_expanded"] / max(info["seconds_device"], 1e-9),
         "expanded_per_s_wall": info["n_expanded"] / wall, "seconds_wall": wall,
+        "cpu_baseline": {"value": cinfo["n_expanded"] / cpu_s, "unit": "nodes expanded/s", "cores": 1, "kind": "port",
+                         "sample": "C oracle bfs, same presentation, budget 2e6 (sequential algorithm, one core)"},
     }
 
 

@@ -56,6 +56,13 @@ def main():
                     wrong.append(k)
             print(f"mrl {mrl}: {len(part)} searches done, solved so far {n_solved}", file=sys.stderr, flush=True)
     wall = time.perf_counter() - t0
+    # CPU baseline beside it: the C oracle on sampled unsolved rows, one core
+    from oracle import oracle as O
+
+    c0 = time.perf_counter()
+    cpu_visited = sum(O.greedy_search(row(k), 100_000)[2]["n_visited"] for k in (533, 700, 900, 1189))
+    cpu_rate = cpu_visited / (time.perf_counter() - c0)
+    print(f"cpu baseline (C oracle, 1 core, 4 unsolved rows at budget 1e5): {cpu_rate:.3e} visited/s", file=sys.stderr)
     print(json.dumps({"config": "greedy_search over 1190 Miller-Schupp presentations", "budget": args.budget,
                       "solved": n_solved, "stored_paths_reproduced": n_path_ok, "mismatching_rows": wrong[:20],
                       "visited_total": visited, "expanded_total": expanded, "seconds_wall": wall,
