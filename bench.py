@@ -318,7 +318,9 @@ def run_b200(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_move": 4 * mrl + 6,
-                "kernel": "acs::ac_step_words_kernel<9,2>" if mrl == 36 else "acs::ac_step_*_kernel",
+                "kernel": ("acs::ac_step_words_kernel<NW=9, TRUSTED=%s, LENS=%s, TR=128>"
+                           % (bool(FLAGS & 2), bool(FLAGS & 4))) if mrl == 36 else "acs::ac_step_*_kernel",
+                "kernel_flags": FLAGS,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
             },
             "cpu_baseline": cpu,

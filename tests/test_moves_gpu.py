@@ -159,8 +159,10 @@ def test_full_size_properties():
     assert np.array_equal(c2[ok], S[ok])
 
 
-def test_env_step_batch_vs_oracle():
-    """acs_env_step_host (device-resident state) == oracle ACEnv.step over 200 steps."""
+@pytest.mark.parametrize("n,steps", [(5000, 60), (300_001, 4)])  # the second spans 3 pipeline chunks
+def test_env_step_batch_vs_oracle(n, steps):
+    """acs_env_step_host (device-resident state, host actions in, host results out, chunked
+    copy/compute pipeline) == oracle ACEnv.step."""
     import ctypes as C
     import torch
     from ac_solver_b200 import _lib
@@ -168,7 +170,7 @@ def test_env_step_batch_vs_oracle():
     L = _lib.lib()
     ctx = _lib.ctx(0)
     rng = np.random.default_rng(11)
-    n, mrl, H = 5000, 36, 50
+    mrl, H = 36, 50
     S = random_rows(rng, n, mrl)
     ref_state = S.copy()
     ref_sc = np.zeros(n, np.int32)
@@ -179,11 +181,11 @@ def test_env_step_batch_vs_oracle():
     done = np.zeros(n, np.uint8)
     trunc = np.zeros(n, np.uint8)
     nbad = C.c_int64(0)
-    for step in range(60):
+    for step in range(steps):
         A = rng.integers(0, 12, size=n).astype(np.uint8)
         _lib.check(L.acs_env_step_host(ctx, d_state.data_ptr(), d_sc.data_ptr(), A.ctypes.data, obs.ctypes.data,
                                        rew.ctypes.data, done.ctypes.data, trunc.ctypes.data, n, mrl, H,
-                                       2 if step >= 30 else 0,  # both kernel variants (states are normalized)
+                                       2 if step >= steps // 2 else 0,  # both kernel variants (states are normalized)
                                        C.byref(nbad)))
         er, ed, et, el, es = O.env_step_batch(ref_state, A, ref_sc, H)
         ok = es == 0
