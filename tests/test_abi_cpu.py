@@ -109,3 +109,34 @@ def test_shard_owner_is_independent_of_table_slot():
             win = ((mine >> np.uint64(shift)) & np.uint64(7)).astype(np.int64)
             c = np.bincount(win, minlength=8)
             assert c.min() > 0.6 * len(mine) / 8, (world, shift, c)
+
+
+def test_vector_env_normal_form_mask_matches_oracle():
+    """The host predicate that gates the steady-state kernel variant in ACVectorEnv must agree with
+    "simplify_presentation(cyclical=True) is the identity" for every row."""
+    from ac_solver_b200.envs.vector_env import _lens_of, _normal_form_mask
+    from ac_solver_b200.synthetic import random_presentations
+    from oracle import oracle as O
+
+    rng = np.random.default_rng(3)
+    mrl, n = 12, 6000
+    S = np.zeros((n, 2 * mrl), np.int8)
+    for h in range(2):
+        L = rng.integers(1, mrl + 1, size=n)
+        w = rng.choice(np.array([-2, -1, 1, 2], np.int8), size=(n, mrl))
+        S[:, h * mrl : (h + 1) * mrl] = np.where(np.arange(mrl)[None, :] < L[:, None], w, 0)
+    S[: n // 3] = random_presentations(n // 3, mrl, seed=1)  # plenty of genuine normal forms
+    mask = _normal_form_mask(S)
+    expect = np.zeros(n, bool)
+    for k in range(n):
+        ok = True
+        for h in range(2):
+            w = S[k, h * mrl : (h + 1) * mrl]
+            r, _ = O.simplify_relator(w, mrl, cyclical=True)
+            ok = ok and np.array_equal(r, w)
+        expect[k] = ok
+    assert np.array_equal(mask, expect)
+    assert 0 < mask.sum() < n
+    lens = _lens_of(S)
+    assert np.array_equal(lens[:, 0], np.count_nonzero(S[:, :mrl], axis=1))
+    assert np.array_equal(lens[:, 1], np.count_nonzero(S[:, mrl:], axis=1))
