@@ -340,6 +340,11 @@ extern "C" int acs_bfs_create(acs_ctx* /*ctx*/, int device, int mrl, int64_t max
     uint64_t t = 1024;
     while (t < 2 * b->cap) t <<= 1;
     b->tcap = t;
+    if (t > (1ull << 31)) {  // slot indices are kept in 32 bits (0xFFFFFFFF = "no slot")
+        delete b;
+        g_bfs_err = "bfs: node budget above 2^30 needs the sharded search (acs_sbfs_*, search/sharded.py)";
+        return ACS_ERR_UNSUPPORTED;
+    }
     b->chunk_cap = std::min<uint64_t>((uint64_t)kMaxChunkParents, b->cap);
     const uint64_t nblocks = (b->chunk_cap + kParentsPerBlock - 1) / kParentsPerBlock;
     b->path_cap = 1 << 16;

@@ -92,6 +92,8 @@ class GpuShardOps:
         while tcap < 2 * self.cap:
             tcap <<= 1
         self.tcap = tcap
+        if tcap > (1 << 31):  # slot indices travel in 32 bits (csrc/sbfs.cu rec_slot)
+            raise _lib.AcsError(f"shard of {self.cap} nodes per rank is too large (table > 2^31 slots): use more GPUs")
         i64 = dict(dtype=torch.int64, device=self.dev)
         self.keys = torch.empty((self.cap, 2 * self.W), **i64)
         self.parent = torch.empty(self.cap, **i64)

@@ -3,9 +3,13 @@
 presentations (one warp per search, one launch per max_relator_length group).
 
     python scripts/greedy_sweep.py [--budget 1000000] [--max-group 400]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29521 scripts/greedy_sweep.py ...        # N GPUs
 
-Checks the outcome against the data shipped with the reference: rows 0..532 are solved with
-exactly the stored paths (greedy_search_paths.txt, action+1 convention), rows 533.. fail."""
+Searches are independent, so with N GPUs rank r takes rows r, r+N, ... of every group (no
+data-path collective; the per-row outcomes are gathered on rank 0 at the end).  The outcome is
+checked against the data shipped with the reference: rows 0..532 are solved with exactly the
+stored paths (greedy_search_paths.txt, action+1 convention), rows 533.. fail."""
 import argparse
 import json
 import os
@@ -23,7 +27,16 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--budget", type=int, default=1_000_000)
     ap.add_argument("--max-group", type=int, default=400)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("gloo")  # only a final gather of small Python objects
     ms = np.load(os.path.join(ROOT, "tests", "golden", "miller_schupp.npz"))
     offs, flat = ms["greedy_path_offsets"], ms["greedy_path_flat"]
 
@@ -32,41 +45,59 @@ def main():
         p = ms["presentations36"][k]
         return np.concatenate([p[:m], p[36 : 36 + m]]).astype(np.int8)
 
-    n_solved = n_path_ok = visited = expanded = 0
-    wrong = []
+    mine = {}  # row index -> (solved, path, n_visited, n_expanded)
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     dev_s = 0.0
     for mrl in sorted(set(int(m) for m in ms["mrl"])):
-        rows = [k for k in range(len(ms["mrl"])) if ms["mrl"][k] == mrl]
+        rows = [k for k in range(len(ms["mrl"])) if ms["mrl"][k] == mrl][rank::world]
         for i in range(0, len(rows), args.max_group):
             part = rows[i : i + args.max_group]
             out = greedy_search_batch(np.stack([row(k) for k in part]), args.budget, path_cap=4096)
             dev_s += out[0][2]["seconds_device"]
             for k, (solved, path, info) in zip(part, out):
-                visited += info["n_visited"]
-                expanded += info["n_expanded"]
-                n_solved += solved
-                if k < 533:
-                    exp = [(int(a) - 1, int(l)) for a, l in flat[offs[k] : offs[k + 1]]]
-                    if solved and path == exp:
-                        n_path_ok += 1
-                    else:
-                        wrong.append(k)
-                elif solved:
-                    wrong.append(k)
-            print(f"mrl {mrl}: {len(part)} searches done, solved so far {n_solved}", file=sys.stderr, flush=True)
+                mine[k] = (solved, path, info["n_visited"], info["n_expanded"])
+        print(f"rank {rank}: mrl {mrl} done ({len(rows)} searches)", file=sys.stderr, flush=True)
+    if dist is not None:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((mine, dev_s), gathered, dst=0)
+        dist.barrier()
+        if rank == 0:
+            mine = {k: v for part, _ in gathered for k, v in part.items()}
+            dev_s = max(d for _, d in gathered)
     wall = time.perf_counter() - t0
-    # CPU baseline beside it: the C oracle on sampled unsolved rows, one core
-    from oracle import oracle as O
+    if rank == 0:
+        n_solved = n_path_ok = visited = expanded = 0
+        wrong = []
+        for k in range(len(ms["mrl"])):
+            solved, path, nv, ne = mine[k]
+            visited += nv
+            expanded += ne
+            n_solved += solved
+            if k < 533:
+                exp = [(int(a) - 1, int(l)) for a, l in flat[offs[k] : offs[k + 1]]]
+                if solved and path == exp:
+                    n_path_ok += 1
+                else:
+                    wrong.append(k)
+            elif solved:
+                wrong.append(k)
+        line = {"config": "greedy_search over 1190 Miller-Schupp presentations", "budget": args.budget, "n_gpus": world,
+                "solved": n_solved, "stored_paths_reproduced": n_path_ok, "mismatching_rows": wrong[:20],
+                "visited_total": visited, "expanded_total": expanded, "seconds_wall": wall,
+                "seconds_device_max_rank": dev_s, "visited_per_s_wall": visited / wall}
+        if not args.no_cpu_baseline:
+            # CPU baseline beside it: the C oracle on sampled unsolved rows, one core
+            from oracle import oracle as O
 
-    c0 = time.perf_counter()
-    cpu_visited = sum(O.greedy_search(row(k), 100_000)[2]["n_visited"] for k in (533, 700, 900, 1189))
-    cpu_rate = cpu_visited / (time.perf_counter() - c0)
-    print(f"cpu baseline (C oracle, 1 core, 4 unsolved rows at budget 1e5): {cpu_rate:.3e} visited/s", file=sys.stderr)
-    print(json.dumps({"config": "greedy_search over 1190 Miller-Schupp presentations", "budget": args.budget,
-                      "solved": n_solved, "stored_paths_reproduced": n_path_ok, "mismatching_rows": wrong[:20],
-                      "visited_total": visited, "expanded_total": expanded, "seconds_wall": wall,
-                      "seconds_device": dev_s, "visited_per_s_device": visited / max(dev_s, 1e-9)}))
+            c0 = time.perf_counter()
+            cpu_visited = sum(O.greedy_search(row(k), 100_000)[2]["n_visited"] for k in (533, 700, 900, 1189))
+            line["cpu_baseline"] = {"value": cpu_visited / (time.perf_counter() - c0), "unit": "visited/s", "cores": 1,
+                                    "kind": "port", "sample": "C oracle greedy, 4 unsolved rows at budget 1e5"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
