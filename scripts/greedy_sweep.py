@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--budget", type=int, default=1_000_000)
     ap.add_argument("--max-group", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=8, help="groups in flight at once (1 = sequential)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dist = None
@@ -50,15 +51,25 @@ def main():
         dist.barrier()
     t0 = time.perf_counter()
     dev_s = 0.0
+    # Every search is a sequential chain on one warp, so a launch lasts as long as its slowest search;
+    # the max_relator_length groups are therefore run CONCURRENTLY (one host thread and one CUDA stream
+    # each, ctypes releases the GIL): the sweep takes the time of the slowest group, not the sum.
+    from concurrent.futures import ThreadPoolExecutor
+
+    def run_group(part):
+        out = greedy_search_batch(np.stack([row(k) for k in part]), args.budget, path_cap=4096)
+        return part, out
+
+    parts = []
     for mrl in sorted(set(int(m) for m in ms["mrl"])):
         rows = [k for k in range(len(ms["mrl"])) if ms["mrl"][k] == mrl][rank::world]
-        for i in range(0, len(rows), args.max_group):
-            part = rows[i : i + args.max_group]
-            out = greedy_search_batch(np.stack([row(k) for k in part]), args.budget, path_cap=4096)
-            dev_s += out[0][2]["seconds_device"]
+        parts += [rows[i : i + args.max_group] for i in range(0, len(rows), args.max_group)]
+    with ThreadPoolExecutor(max_workers=max(1, args.streams)) as pool:
+        for part, out in pool.map(run_group, parts):
+            dev_s = max(dev_s, out[0][2]["seconds_device"])
             for k, (solved, path, info) in zip(part, out):
                 mine[k] = (solved, path, info["n_visited"], info["n_expanded"])
-        print(f"rank {rank}: mrl {mrl} done ({len(rows)} searches)", file=sys.stderr, flush=True)
+    print(f"rank {rank}: {len(parts)} groups done", file=sys.stderr, flush=True)
     if dist is not None:
         gathered = [None] * world if rank == 0 else None
         dist.gather_object((mine, dev_s), gathered, dst=0)
