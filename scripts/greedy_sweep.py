@@ -38,7 +38,8 @@ def main():
 
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         dist.init_process_group("gloo")  # only a final gather of small Python objects
-    ms = np.load(os.path.join(ROOT, "tests", "golden", "miller_schupp.npz"))
+    with np.load(os.path.join(ROOT, "tests", "golden", "miller_schupp.npz")) as f:
+        ms = {k: f[k] for k in f.files}  # materialised: NpzFile's lazy zip reads are not thread-safe
     offs, flat = ms["greedy_path_offsets"], ms["greedy_path_flat"]
 
     def row(k):
