@@ -116,10 +116,11 @@ def test_moves_batch_edge_cases():
 
 def test_full_size_properties():
     """BASELINE config 2 size (1 Mi rows, mrl 36): size-independent properties.
-    (a) a conjugation followed by the inverse conjugation restores every cyclically reduced
-    state; (b) r1 -> r1 r0 followed by r1 -> r1 r0^-1 restores rows where both were accepted;
-    (c) lengths returned == non-zero counts of the returned rows; (d) idempotence of the
-    trailing simplification: applying a rejected move twice changes nothing."""
+    (a) without cyclic reduction, g(.)g^-1 followed by g^-1(.)g is the identity whenever the first
+    move is accepted; (b) with cyclic reduction a conjugation of a cyclically reduced word is a
+    rotation by at most one letter (lengths, letter multisets and the other relator preserved);
+    (c) lengths returned == non-zero counts of the returned rows; (d) r1 -> r1 r0 followed by
+    r1 -> r1 r0^-1 restores every row where the first move was accepted."""
     from ac_solver_b200 import ac_moves_batch
 
     rng = np.random.default_rng(0)
