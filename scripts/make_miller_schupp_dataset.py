@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Regenerate the Miller-Schupp dataset files with THIS framework (GPU): the 1190 presentations
+MS(n, w), n = 1..7, |w| <= 7, the greedy-solved subset with its paths (budget 1e6) and the
+BFS-solved subset (budget 1e6), in the on-disk formats of the reference's
+``ac_solver/search/miller_schupp/data/*.txt`` (one Python literal per line).
+
+    python scripts/make_miller_schupp_dataset.py [--out ac_solver_b200/search/miller_schupp/data]
+
+File conventions reproduced from the reference's shipped data:
+  all_presentations.txt            greedy-solved rows first, then the unsolved ones, each block in
+                                   generation order (n-major, then |w|, then enumeration order)
+  greedy_solved_presentations.txt  the first block
+  greedy_search_paths.txt          one path per solved row, stored as (action + 1, length) with
+                                   head (0, L0) -- the older 1-based move numbering of the data file
+  bfs_solved_presentations.txt     rows bfs() solves, in all_presentations order
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from ac_solver_b200.search.breadth_first import bfs_device  # noqa: E402
+from ac_solver_b200.search.greedy import greedy_search_batch  # noqa: E402
+from ac_solver_b200.search.miller_schupp import (generate_miller_schupp_presentations,  # noqa: E402
+                                                  write_list_to_text_file)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "ac_solver_b200", "search", "miller_schupp", "data"))
+    ap.add_argument("--budget", type=int, default=1_000_000)
+    ap.add_argument("--bfs-budget", type=int, default=1_000_000)
+    args = ap.parse_args()
+    t0 = time.perf_counter()
+    rows = []
+    for n in range(1, 8):
+        g = generate_miller_schupp_presentations(n, 7)
+        for lenw in range(1, 8):
+            rows += g.get(lenw, [])
+    assert len(rows) == 1190
+    by_width = {}
+    for k, r in enumerate(rows):
+        by_width.setdefault(len(r), []).append(k)
+
+    def run(ks):
+        return ks, greedy_search_batch(np.array([rows[k] for k in ks], dtype=np.int8), args.budget, path_cap=4096)
+
+    result = {}
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        for ks, out in pool.map(run, list(by_width.values())):
+            for k, (solved, path, info) in zip(ks, out):
+                result[k] = (solved, path)
+    solved = [k for k in range(len(rows)) if result[k][0]]
+    unsolved = [k for k in range(len(rows)) if not result[k][0]]
+    ordered = solved + unsolved
+    t1 = time.perf_counter()
+    bfs_solved = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k in ordered:
+            if bfs_device(np.array(rows[k], dtype=np.int8), args.bfs_budget)[0]:
+                bfs_solved.append(k)
+    t2 = time.perf_counter()
+    os.makedirs(args.out, exist_ok=True)
+    write_list_to_text_file([rows[k] for k in ordered], os.path.join(args.out, "all_presentations"))
+    write_list_to_text_file([rows[k] for k in solved], os.path.join(args.out, "greedy_solved_presentations"))
+    write_list_to_text_file([[(a + 1, l) for a, l in result[k][1]] for k in solved],
+                            os.path.join(args.out, "greedy_search_paths"))
+    write_list_to_text_file([rows[k] for k in bfs_solved], os.path.join(args.out, "bfs_solved_presentations"))
+    print(json.dumps({"presentations": len(rows), "greedy_solved": len(solved), "bfs_solved": len(bfs_solved),
+                      "seconds_generate_and_greedy": t1 - t0, "seconds_bfs": t2 - t1, "out": args.out}))
+
+
+if __name__ == "__main__":
+    main()
