@@ -111,3 +111,13 @@ def load_presentations_from_text_file(path):
 
     with open(path) as f:
         return [literal_eval(line.strip()) for line in f if line.strip()]
+
+
+def load_initial_states_from_text_file(states_type):
+    """Mirror of the reference's ``ac_solver/agents/utils.py:10-34``: the shipped presentations,
+    sorted by hardness (greedy-solved first).  states_type: "solved" or "all"."""
+    assert states_type in ["solved", "all"], "states_type must be 'solved' or 'all'"
+    name = ("greedy_solved" if states_type == "solved" else "all") + "_presentations.txt"
+    states = load_presentations_from_text_file(os.path.join(os.path.dirname(os.path.realpath(__file__)), "data", name))
+    print(f"Loaded {len(states)} presentations from {name}.")
+    return states
