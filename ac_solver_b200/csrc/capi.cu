@@ -92,9 +92,15 @@ int acs_ctx_create(int device, acs_ctx** out) {
     ACS_CUDA(cudaSetDevice(device));
     acs_ctx* c = new acs_ctx();
     c->device = device;
-    for (int k = 0; k < kStreams; ++k) ACS_CUDA(cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking));
-    ACS_CUDA(cudaMalloc(&c->d_err, 2 * sizeof(unsigned long long)));
-    ACS_CUDA(cudaMallocHost(&c->h_err, 2 * sizeof(unsigned long long)));
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < kStreams && e == cudaSuccess; ++k)
+        e = cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&c->d_err, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_err, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {  // release whatever was created
+        acs_ctx_destroy(c);
+        return cuda_fail(e, "acs_ctx_create");
+    }
     *out = c;
     return ACS_OK;
 }
