@@ -99,6 +99,16 @@ _SIGS = {
     "acs_sbfs_lower_bound": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "acs_sbfs_lookup": (C.c_int, [_P, C.c_int64, _P, _P]),
     "acs_sbfs_unpack": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    "acs_pbfs_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.POINTER(_P)]),
+    "acs_pbfs_export": (C.c_int, [_P, _P]),
+    "acs_pbfs_connect": (C.c_int, [_P, C.c_char_p]),
+    "acs_pbfs_connect_local": (C.c_int, [_P, C.c_int]),
+    "acs_pbfs_run": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.POINTER(SearchResult)]),
+    "acs_pbfs_lookup": (C.c_int, [_P, C.c_int64, _P]),
+    "acs_pbfs_visited": (C.c_int, [_P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "acs_pbfs_stats": (C.c_int, [_P, _P]),
+    "acs_pbfs_set_timeout": (C.c_int, [_P, C.c_double]),
+    "acs_pbfs_destroy": (None, [_P]),
 }
 
 

@@ -1,0 +1,1378 @@
+// pbfs.cu -- hash-partitioned breadth-first search of the AC graph, native driver.
+//
+// Contract (reference, paths relative to /root/reference): ac_solver/search/breadth_first.py:15-97
+// -- FIFO order, children in action order, "solved" test before the visited test, budget test
+// after each node's 12 children.  Result, visited ARRAY (order included), "New minimal length"
+// sequence and counters are identical to the sequential reference for every world size.
+//
+// Design (B200-first; nothing here is host Python, and nothing in the chunk loop syncs with the
+// host).  The visited set and the node store are partitioned by owner(state) = hash(key) -> rank.
+// Nodes carry GLOBAL ids equal to their FIFO position.  The search advances in chunks of
+// consecutive global ids [head, head+F); one chunk is this stream-ordered pipeline on every rank:
+//
+//   prep     local parent range [l0,l1) of the chunk, reset of cursors / control block / bitmap
+//   expand   one thread per owned parent, a warp = 32 parents stepping through the 12 moves
+//            together (uniform control flow).  Children are labelled with the chunk-local
+//            candidate id c = 12*(gid-head)+action and appended to per-warp, per-destination
+//            shared-memory queues; a full queue (32 records) is flushed with ONE coalesced
+//            512-byte burst of peer stores straight into the owner rank's inbox over NVLink
+//            (the compute step and the all-to-all are one kernel; there is no pack, no count
+//            exchange and no send buffer).  Each (source, destination) pair owns a fixed inbox
+//            region, so the write cursors are local atomics.
+//   signal/wait   every rank stores its control block (minima for solved / raising child /
+//            first occurrence of each total length, record counts) into every peer's control
+//            inbox and publishes an epoch flag with st.release.sys; a one-block kernel spins on
+//            the G flags with ld.acquire.sys (bounded by a timeout).  No NCCL, no host.
+//   insert   owner side: one thread per received record; exact open-addressing table of 8-byte
+//            slots probed a 32-byte sector (4 slots) at a time; "smallest candidate id wins" by
+//            atomicMin on tentative slots.  A claim flips bit c of the winner bitmap, a displaced
+//            claim flips it back (XOR is order independent), so no second pass over the table.
+//   signal/wait
+//   scan     OR of all ranks' winner bitmaps by peer loads, popcount prefix sums (global and
+//            local) -> every winner's global id and local index
+//   decide   one block, identical on every rank (replicated data => identical decisions): budget
+//            cut by binary search in the prefix sums, solved / raising child, minimal-length
+//            log, counters, next chunk.  Writes the device-resident state read by all kernels.
+//   commit   winners below the limit are appended (key, parent link, global id) and their table
+//            slots re-pointed at the node.
+// Inboxes, control inboxes and bitmaps are double buffered by chunk parity, so a rank may run
+// one pipeline stage ahead of its peers without overwriting what they still read.  The host
+// enqueues chunk pipelines ahead of the device and only looks at a lagging copy of the state.
+//
+// One process per GPU: the exchange arena is shared with cudaIpc handles (acs_pbfs_export /
+// acs_pbfs_connect); for tests all shards may also live in one process (acs_pbfs_connect_local),
+// on one device (kernels of the shards are then serialised on one stream) or on several.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/acsolver_b200.h"
+#include "ac_core.cuh"
+#include "ac_keys.cuh"
+#include "acs_internal.h"
+
+namespace acs {
+
+constexpr int kPbMaxWorld = 16;
+constexpr int kCtrlWords = 136;        // sol, err, first_len[128], count, ierr, pad
+constexpr int kCtrlSol = 0, kCtrlErr = 1, kCtrlLen0 = 2, kCtrlCount = 130, kCtrlIerr = 131;
+constexpr uint64_t kTent = 1ull << 63;  // tentative slot: bit 63 | c:30 << 33 | record:27 << 6 | fp:6
+constexpr int kCBits = 30, kRecBits = 27;
+constexpr uint64_t kCMask = (1ull << kCBits) - 1, kRecMask = (1ull << kRecBits) - 1;
+constexpr uint32_t kNoSlotPb = 0xFFFFFFFFu;
+constexpr int kQueue = 64;              // per-warp, per-destination staging ring (records)
+constexpr int kScanT = 256, kScanPer = 8, kScanBlock = kScanT * kScanPer;  // words per scan block
+
+enum : int { IERR_PAIR_OVERFLOW = 1, IERR_TABLE_FULL = 2, IERR_SHARD_FULL = 4, IERR_TIMEOUT = 8 };
+
+// Device-resident run state of one rank.  Every scalar decision is replicated on all ranks.
+struct PbState {
+    // constants of the run
+    int64_t budget, cap_local, chunk_cap, pair_cap;
+    uint64_t tmask;
+    int32_t mrl, cyclical, world, rank;
+    // current chunk
+    int64_t head, F, n_nodes, n_local, l0, l1, level_end;
+    uint64_t epoch;        // chunk counter, monotone across runs (flags carry it)
+    int32_t buf, min_len, levels, done;
+    // decided for the commit of the current chunk
+    int64_t limit, n_nodes0, n_local0, head0;
+    int32_t commit_pending, pad1;
+    // results
+    int64_t n_expanded, sol_gid, err_code, chunks;
+    int32_t solved, budget_hit, status, ierr, n_minlen, pad0;
+    int32_t minlen_log[128];
+    unsigned long long records_sent, records_recv;  // statistics
+};
+
+// Pointers of one rank.  The "arena" part is visible to the peers (IPC or same process).
+struct PbShard {
+    PbState* st;
+    uint64_t* keys;      // [cap][2W]
+    int64_t* parent;     // [cap]
+    int64_t* gid;        // [cap]
+    uint64_t* table;     // [tmask+1]
+    uint32_t* rec_slot;  // [world*pair_cap]
+    uint32_t* bitmap_global;
+    uint32_t* prefix_global;  // [words+1]
+    uint32_t* prefix_local;   // [words+1]
+    uint32_t* block_sums;     // [2][nblk]
+    unsigned long long* cursors;     // [world]
+    unsigned long long* ctrl_local;  // [kCtrlWords]
+    // arena (same layout on every rank)
+    char* arena;                     // own
+    char* peer[kPbMaxWorld];         // peer arenas as seen from this process
+    int64_t off_flags;               // [2][world] u64
+    int64_t off_ctrl;                // [2 buf][world][kCtrlWords] u64
+    int64_t off_bitmap;              // [2 buf][bitmap_words] u32
+    int64_t off_keys;                // [2 buf][world][pair_cap][2W] u64
+    int64_t off_c;                   // [2 buf][world][pair_cap] u32
+    int64_t bitmap_words, nblk;
+    int32_t W, world, rank, pad;
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- hashing: slot = low bits, committed fingerprint = bits 41..63, tentative fp = bits 58..63,
+// owner from a separately mixed product (must be independent of the slot bits, see sbfs.cu) ----
+template <int W>
+__host__ __device__ __forceinline__ uint64_t pb_hash(const Key<W>& q) {
+    uint64_t h = q.k[0] * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 32;
+#pragma unroll
+    for (int i = 1; i < 2 * W; ++i) {
+        h = (h + q.k[i]) * 0xD6E8FEB86659FD93ull;
+        h ^= h >> 29;
+    }
+    h *= 0xC4CEB9FE1A85EC53ull;
+    h ^= h >> 32;
+    return h;
+}
+__host__ __device__ __forceinline__ int pb_owner(uint64_t h, int world) {
+    const uint32_t m = (uint32_t)((h * 0xFF51AFD7ED558CCDull) >> 32);
+    return (int)(((uint64_t)m * (uint32_t)world) >> 32);
+}
+
+template <int W>
+__device__ __forceinline__ Key<W> load_key_cg(const uint64_t* keys, uint64_t idx) {
+    Key<W> q;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2*>(keys) + W * idx + i);
+        q.k[2 * i] = v.x;
+        q.k[2 * i + 1] = v.y;
+    }
+    return q;
+}
+
+__device__ __forceinline__ uint64_t* sh_flags(const PbShard& S, char* base, int kind) {
+    return reinterpret_cast<uint64_t*>(base + S.off_flags) + kind * S.world;
+}
+__device__ __forceinline__ unsigned long long* sh_ctrl(const PbShard& S, char* base, int buf, int src) {
+    return reinterpret_cast<unsigned long long*>(base + S.off_ctrl) + ((int64_t)buf * S.world + src) * kCtrlWords;
+}
+__device__ __forceinline__ uint32_t* sh_bitmap(const PbShard& S, char* base, int buf) {
+    return reinterpret_cast<uint32_t*>(base + S.off_bitmap) + (int64_t)buf * S.bitmap_words;
+}
+__device__ __forceinline__ uint64_t* sh_keys(const PbShard& S, char* base, int buf, int64_t pair_cap) {
+    return reinterpret_cast<uint64_t*>(base + S.off_keys) + (int64_t)buf * S.world * pair_cap * 2 * S.W;
+}
+__device__ __forceinline__ uint32_t* sh_c(const PbShard& S, char* base, int buf, int64_t pair_cap) {
+    return reinterpret_cast<uint32_t*>(base + S.off_c) + (int64_t)buf * S.world * pair_cap;
+}
+
+// ---- prep ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pb_prep_kernel(const PbShard S) {
+    PbState* st = S.st;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->commit_pending = 0;  // set again by this chunk's decide
+    if (st->done) return;
+    const int64_t nwords = (12 * st->F + 31) / 32;
+    uint32_t* bm = sh_bitmap(S, S.arena, st->buf);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x)
+        bm[i] = 0;
+    if (blockIdx.x != 0) return;
+    if (threadIdx.x < S.world) S.cursors[threadIdx.x] = 0;
+    if (threadIdx.x < kCtrlWords)
+        S.ctrl_local[threadIdx.x] = (threadIdx.x == kCtrlCount || threadIdx.x == kCtrlIerr) ? 0ull : ~0ull;
+    if (threadIdx.x == 0) {
+        // owned parents of [head, head+F): gid[] is increasing, the range starts where the last ended
+        const int64_t l0 = st->l1, want = st->head + st->F;
+        int64_t lo = l0, hi = st->n_local;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (S.gid[mid] < want) lo = mid + 1;
+            else hi = mid;
+        }
+        st->l0 = l0;
+        st->l1 = lo;
+    }
+}
+
+// ---- expand ----------------------------------------------------------------------------------
+// Per-warp staging: for every destination a ring of kQueue records (key + candidate id).
+template <int W>
+struct WarpQueues {
+    uint64_t* keys;  // [world][kQueue][2W]
+    uint32_t* c;     // [world][kQueue]
+    uint32_t* cnt;   // [world]
+    uint32_t* head;  // [world] 0 or 32
+};
+template <int W>
+__host__ __device__ constexpr size_t queue_bytes_per_warp(int world) {
+    return (size_t)world * (kQueue * (16 * W + 4) + 8);
+}
+
+template <int W>
+__device__ __forceinline__ void pb_flush(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int d, uint32_t n,
+                                         int lane) {
+    // n <= 32 records from the head of ring d go to rank d's inbox region (me -> d)
+    unsigned long long pos = 0;
+    if (lane == 0) pos = atomicAdd(&S.cursors[d], (unsigned long long)n);
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    const uint32_t hd = Q.head[d];
+    if (pos + n > (unsigned long long)st->pair_cap) {
+        if (lane == 0) atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_PAIR_OVERFLOW);
+    } else if ((uint32_t)lane < n) {
+        const uint32_t q = (hd + lane) & (kQueue - 1);
+        char* base = S.peer[d];
+        const int64_t r = (int64_t)S.rank * st->pair_cap + (int64_t)pos + lane;
+        uint64_t* dk = sh_keys(S, base, st->buf, st->pair_cap) + r * 2 * W;
+        const uint64_t* sk = Q.keys + ((size_t)d * kQueue + q) * 2 * W;
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+            reinterpret_cast<ulonglong2*>(dk)[i] = make_ulonglong2(sk[2 * i], sk[2 * i + 1]);
+        sh_c(S, base, st->buf, st->pair_cap)[r] = Q.c[d * kQueue + q];
+    }
+    __syncwarp();
+    if (lane == 0) {
+        Q.head[d] = (hd + n) & (kQueue - 1);
+        Q.cnt[d] -= n;
+    }
+    __syncwarp();
+}
+
+template <int W>
+__device__ __noinline__ void pb_enqueue(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int dest,
+                                        const Key<W>& child, uint32_t c, int lane) {
+    const int world = S.world;
+    for (int d = 0; d < world; ++d) {
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, dest == d);
+        if (mask == 0) continue;
+        const uint32_t base = Q.cnt[d];
+        if (dest == d) {
+            const uint32_t q = (Q.head[d] + base + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
+            uint64_t* sk = Q.keys + ((size_t)d * kQueue + q) * 2 * W;
+#pragma unroll
+            for (int i = 0; i < 2 * W; ++i) sk[i] = child.k[i];
+            Q.c[d * kQueue + q] = c;
+        }
+        __syncwarp();
+        const uint32_t total = base + __popc(mask);
+        if (lane == 0) Q.cnt[d] = total;
+        __syncwarp();
+        if (total >= 32) pb_flush<W>(S, st, Q, d, 32, lane);
+    }
+}
+
+template <int W, bool TRUSTED>
+__global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int warps_per_block) {
+    const PbState* st = S.st;
+    if (st->done) return;
+    extern __shared__ __align__(16) unsigned char pb_smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int world = S.world;
+    WarpQueues<W> Q;
+    {
+        unsigned char* p = pb_smem + (size_t)wib * queue_bytes_per_warp<W>(world);
+        Q.keys = reinterpret_cast<uint64_t*>(p);
+        p += (size_t)world * kQueue * 16 * W;
+        Q.c = reinterpret_cast<uint32_t*>(p);
+        p += (size_t)world * kQueue * 4;
+        Q.cnt = reinterpret_cast<uint32_t*>(p);
+        Q.head = Q.cnt + world;
+    }
+    if (lane < world) {
+        Q.cnt[lane] = 0;
+        Q.head[lane] = 0;
+    }
+    __syncwarp();
+    const int64_t l1 = st->l1;
+    const uint64_t head = (uint64_t)st->head;
+    const int mrl = st->mrl;
+    const bool cyc = st->cyclical != 0;
+    const int min_len = st->min_len;
+    const int64_t gw = (int64_t)blockIdx.x * warps_per_block + wib, nw = (int64_t)gridDim.x * warps_per_block;
+    unsigned long long sent = 0;
+    for (int64_t base = st->l0 + 32 * gw; base < l1; base += 32 * nw) {
+        const int64_t j = base + lane;
+        const bool valid = j < l1;
+        Key<W> pk;
+#pragma unroll
+        for (int i = 0; i < 2 * W; ++i) pk.k[i] = 0;
+        uint64_t pg = 0;
+        if (valid) {
+            pk = load_key<W>(S.keys, (uint64_t)j);
+            pg = (uint64_t)S.gid[j];
+        }
+        Rel<2 * W> p0, p1;
+        split_key<W>(pk, p0, p1);
+        const uint32_t cbase = (uint32_t)((pg - head) * 12);
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+            Rel<2 * W> r0 = p0, r1 = p1;
+            int dest = -1;
+            Key<W> child;
+#pragma unroll
+            for (int i = 0; i < 2 * W; ++i) child.k[i] = 0;
+            if (valid) {
+                bool co;
+                const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
+                const uint64_t gidc = pg * 12 + a;
+                if (stt != ST_OK) {
+                    atomicMin(&S.ctrl_local[kCtrlErr], (unsigned long long)((gidc << 2) | (unsigned)stt));
+                } else {
+                    const int L = r0.len + r1.len;
+                    if (L < min_len) atomicMin(&S.ctrl_local[kCtrlLen0 + L], (unsigned long long)gidc);
+                    if (L == 2) atomicMin(&S.ctrl_local[kCtrlSol], (unsigned long long)gidc);  // before the visited test
+                    child = make_key<W>(r0, r1);
+                    if (!key_eq<W>(child, pk)) {
+                        dest = world > 1 ? pb_owner(pb_hash<W>(child), world) : 0;
+                        ++sent;
+                    }
+                }
+            }
+            pb_enqueue<W>(S, st, Q, dest, child, cbase + a, lane);
+        }
+    }
+    for (int d = 0; d < world; ++d) {
+        const uint32_t n = Q.cnt[d];
+        if (n) pb_flush<W>(S, st, Q, d, n, lane);
+    }
+    // the peer stores of this thread are performed before anything a later kernel publishes
+    __threadfence_system();
+#pragma unroll
+    for (int off = 16; off; off >>= 1) sent += __shfl_xor_sync(0xFFFFFFFFu, sent, off);
+    if (lane == 0 && sent) atomicAdd(&S.st->records_sent, sent);
+}
+
+// ---- signal / wait ---------------------------------------------------------------------------
+// kind 0: "my records and control block for this chunk are in your inbox"
+// kind 1: "my winner bitmap for this chunk is final"
+__global__ void __launch_bounds__(256) pb_signal_kernel(const PbShard S, int kind) {
+    const PbState* st = S.st;
+    if (st->done) return;
+    const int world = S.world;
+    if (kind == 0) {
+        for (int i = threadIdx.x; i < world * kCtrlWords; i += blockDim.x) {
+            const int d = i / kCtrlWords, w = i % kCtrlWords;
+            unsigned long long v = S.ctrl_local[w];
+            if (w == kCtrlCount) v = S.cursors[d];
+            if (w == kCtrlIerr) v |= (unsigned long long)st->ierr;
+            sh_ctrl(S, S.peer[d], st->buf, S.rank)[w] = v;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) st_release_sys(sh_flags(S, S.peer[threadIdx.x], kind) + S.rank, st->epoch + 1);
+}
+
+__global__ void __launch_bounds__(32) pb_wait_kernel(const PbShard S, int kind, unsigned long long timeout_ns) {
+    PbState* st = S.st;
+    if (st->done) return;
+    if (threadIdx.x < S.world) {
+        const uint64_t* f = sh_flags(S, S.arena, kind) + threadIdx.x;
+        const uint64_t want = st->epoch + 1;
+        const uint64_t t0 = global_ns();
+        while (ld_acquire_sys(f) < want) {
+            if (global_ns() - t0 > timeout_ns) {
+                atomicOr(&st->ierr, IERR_TIMEOUT);
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+}
+
+// ---- insert ----------------------------------------------------------------------------------
+struct RegionMap {
+    unsigned long long start[kPbMaxWorld + 1];  // prefix of the per-source record counts
+};
+__device__ __forceinline__ void load_regions(const PbShard& S, const PbState* st, RegionMap* R) {
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int s = 0; s < S.world; ++s) {
+            R->start[s] = run;
+            unsigned long long n = __ldcg(&sh_ctrl(S, S.arena, st->buf, s)[kCtrlCount]);
+            if (n > (unsigned long long)st->pair_cap) n = (unsigned long long)st->pair_cap;  // overflow is flagged by the sender
+            run += n;
+        }
+        for (int s = S.world; s <= kPbMaxWorld; ++s) R->start[s] = run;
+    }
+    __syncthreads();
+}
+// virtual record index v (0 <= v < total) -> flat inbox index src*pair_cap + offset
+__device__ __forceinline__ int64_t region_index(const RegionMap* R, int world, int64_t pair_cap, unsigned long long v) {
+    int s = 0;
+#pragma unroll 1
+    for (int k = 1; k < world; ++k) s += (v >= R->start[k]) ? 1 : 0;
+    return (int64_t)s * pair_cap + (int64_t)(v - R->start[s]);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
+    PbState* st = S.st;
+    if (st->done) return;
+    __shared__ RegionMap R;
+    load_regions(S, st, &R);
+    const unsigned long long total = R.start[S.world];
+    const int64_t pair_cap = st->pair_cap;
+    const uint64_t* in_keys = sh_keys(S, S.arena, st->buf, pair_cap);
+    const uint32_t* in_c = sh_c(S, S.arena, st->buf, pair_cap);
+    uint32_t* bm = sh_bitmap(S, S.arena, st->buf);
+    const uint64_t tmask = st->tmask;
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->records_recv += total;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+        const int64_t i = region_index(&R, S.world, pair_cap, v);
+        const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
+        const uint32_t c = __ldcg(in_c + i);
+        const uint64_t h = pb_hash<W>(key);
+        const uint64_t fp23 = h >> 41, fp6 = h >> 58;
+        const uint64_t mine = kTent | ((uint64_t)c << 33) | ((uint64_t)i << 6) | fp6;
+        uint64_t s = (h & tmask) & ~3ull;
+        uint32_t my_slot = kNoSlotPb;
+        uint64_t probes = 0;
+        bool finished = false;
+        while (!finished) {
+            const ulonglong2 v01 = __ldcg(reinterpret_cast<const ulonglong2*>(S.table + s));
+            const ulonglong2 v23 = __ldcg(reinterpret_cast<const ulonglong2*>(S.table + s + 2));
+            const uint64_t vv[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+            for (int jj = 0; jj < 4 && !finished; ++jj) {
+                uint64_t cur = vv[jj];
+                const uint64_t slot = s + jj;
+                if (cur == 0) {
+                    cur = atomicCAS((unsigned long long*)&S.table[slot], 0ull, (unsigned long long)mine);
+                    if (cur == 0) {
+                        my_slot = (uint32_t)slot;
+                        atomicXor(&bm[c >> 5], 1u << (c & 31));
+                        finished = true;
+                        break;
+                    }
+                }
+                if (!(cur & kTent)) {  // committed node
+                    if ((cur >> 40) == fp23) {
+                        const Key<W> other = load_key<W>(S.keys, (cur & kIdxMask) - 1);
+                        if (key_eq<W>(other, key)) finished = true;  // already visited
+                    }
+                } else if ((cur & 63ull) == fp6) {  // tentative record of this chunk
+                    const Key<W> other = load_key_cg<W>(in_keys, (cur >> 6) & kRecMask);
+                    if (key_eq<W>(other, key)) {
+                        const uint64_t old = atomicMin((unsigned long long*)&S.table[slot], (unsigned long long)mine);
+                        if (old > mine) {  // this record displaced `old` (same key, larger candidate id)
+                            const uint32_t co = (uint32_t)((old >> 33) & kCMask);
+                            atomicXor(&bm[co >> 5], 1u << (co & 31));
+                            atomicXor(&bm[c >> 5], 1u << (c & 31));
+                            my_slot = (uint32_t)slot;
+                        }
+                        finished = true;
+                    }
+                }
+            }
+            if (!finished) {
+                s = (s + 4) & tmask;
+                probes += 4;
+                if (probes > tmask) {  // cannot happen with the chunk sizing (table <= 3/4 full)
+                    atomicOr(&st->ierr, IERR_TABLE_FULL);
+                    finished = true;
+                }
+            }
+        }
+        S.rec_slot[i] = my_slot;
+    }
+}
+
+// ---- scan ------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_sum2(uint32_t& a, uint32_t& b) {
+    __shared__ uint32_t wa[kScanT / 32], wb[kScanT / 32];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+        a += __shfl_xor_sync(0xFFFFFFFFu, a, off);
+        b += __shfl_xor_sync(0xFFFFFFFFu, b, off);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        wa[wid] = a;
+        wb[wid] = b;
+    }
+    __syncthreads();
+    a = b = 0;
+#pragma unroll
+    for (int w = 0; w < kScanT / 32; ++w) {
+        a += wa[w];
+        b += wb[w];
+    }
+}
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t& total) {
+    __shared__ uint32_t ws[kScanT / 32];
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, off);
+        if (lane >= off) x += t;
+    }
+    __syncthreads();
+    if (lane == 31) ws[wid] = x;
+    __syncthreads();
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kScanT / 32; ++w) {
+        const uint32_t s = ws[w];
+        if (w < (int)wid) before += s;
+        tot += s;
+    }
+    total = tot;
+    return before + x - v;
+}
+
+// OR of every rank's winner bitmap (peer loads) -> bitmap_global; popcount sums per scan block
+__global__ void __launch_bounds__(kScanT) pb_scan_sums_kernel(const PbShard S) {
+    const PbState* st = S.st;
+    if (st->done) return;
+    const int64_t nwords = (12 * st->F + 31) / 32;
+    const int64_t nblk = (nwords + kScanBlock - 1) / kScanBlock;
+    const uint32_t* mine = sh_bitmap(S, S.arena, st->buf);
+    for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+        uint32_t sg = 0, sl = 0;
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
+            if (i < nwords) {
+                const uint32_t loc = __ldcg(mine + i);
+                uint32_t g = loc;
+                for (int r = 0; r < S.world; ++r)
+                    if (r != S.rank) g |= __ldcv(sh_bitmap(S, S.peer[r], st->buf) + i);
+                S.bitmap_global[i] = g;
+                sg += __popc(g);
+                sl += __popc(loc);
+            }
+        }
+        block_sum2(sg, sl);
+        if (threadIdx.x == 0) {
+            S.block_sums[b] = sg;
+            S.block_sums[S.nblk + b] = sl;
+        }
+        __syncthreads();
+    }
+}
+// single block: exclusive scans of both block-sum arrays in place; totals to prefix[nwords]
+__global__ void __launch_bounds__(kScanT) pb_scan_top_kernel(const PbShard S) {
+    const PbState* st = S.st;
+    if (st->done) return;
+    const int64_t nwords = (12 * st->F + 31) / 32;
+    const int64_t nblk = (nwords + kScanBlock - 1) / kScanBlock;
+    for (int which = 0; which < 2; ++which) {
+        uint32_t* sums = S.block_sums + which * S.nblk;
+        uint32_t carry = 0;
+        for (int64_t base = 0; base < nblk; base += kScanT) {
+            const int64_t i = base + threadIdx.x;
+            const uint32_t v = i < nblk ? sums[i] : 0u;
+            uint32_t total;
+            const uint32_t ex = block_excl_scan(v, total);
+            if (i < nblk) sums[i] = carry + ex;
+            carry += total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) (which == 0 ? S.prefix_global : S.prefix_local)[nwords] = carry;
+    }
+}
+__global__ void __launch_bounds__(kScanT) pb_scan_final_kernel(const PbShard S) {
+    const PbState* st = S.st;
+    if (st->done) return;
+    const int64_t nwords = (12 * st->F + 31) / 32;
+    const int64_t nblk = (nwords + kScanBlock - 1) / kScanBlock;
+    const uint32_t* loc = sh_bitmap(S, S.arena, st->buf);
+    for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const int64_t first = b * kScanBlock + (int64_t)threadIdx.x * kScanPer;
+        uint32_t cg[kScanPer], cl[kScanPer];
+        uint32_t sg = 0, sl = 0;
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            const bool in = first + k < nwords;
+            cg[k] = in ? __popc(S.bitmap_global[first + k]) : 0u;
+            cl[k] = in ? __popc(__ldcg(loc + first + k)) : 0u;
+            sg += cg[k];
+            sl += cl[k];
+        }
+        uint32_t tg, tl;
+        uint32_t rg = S.block_sums[b] + block_excl_scan(sg, tg);
+        __syncthreads();
+        uint32_t rl = S.block_sums[S.nblk + b] + block_excl_scan(sl, tl);
+#pragma unroll
+        for (int k = 0; k < kScanPer; ++k) {
+            if (first + k < nwords) {
+                S.prefix_global[first + k] = rg;
+                S.prefix_local[first + k] = rl;
+            }
+            rg += cg[k];
+            rl += cl[k];
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t bm_rank(const uint32_t* bitmap, const uint32_t* prefix, uint64_t c) {
+    const uint32_t r = (uint32_t)(c & 31);
+    return prefix[c >> 5] + (r ? __popc(bitmap[c >> 5] & ((1u << r) - 1u)) : 0u);
+}
+
+// ---- decide ----------------------------------------------------------------------------------
+// Same arithmetic on every rank (all inputs are replicated): see the sequential rules in
+// SURVEY.md Appendix B, generalised from levels to chunks.
+__global__ void __launch_bounds__(kCtrlWords) pb_decide_kernel(const PbShard S) {
+    PbState* st = S.st;
+    if (st->done) return;
+    __shared__ unsigned long long red[kCtrlWords];
+    {
+        const int w = threadIdx.x;
+        unsigned long long v = (w == kCtrlIerr || w == kCtrlCount) ? 0ull : ~0ull;
+        for (int s = 0; s < S.world; ++s) {
+            const unsigned long long x = __ldcg(&sh_ctrl(S, S.arena, st->buf, s)[w]);
+            if (w == kCtrlIerr) v |= x;
+            else if (w == kCtrlCount) v += x;
+            else v = x < v ? x : v;
+        }
+        red[w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const uint32_t* bl = sh_bitmap(S, S.arena, st->buf);
+    const uint64_t F = (uint64_t)st->F, head = (uint64_t)st->head, n_nodes = (uint64_t)st->n_nodes;
+    const uint64_t budget = (uint64_t)st->budget;
+    const int64_t nwords = (12 * (int64_t)F + 31) / 32;
+    const uint64_t total = S.prefix_global[nwords];
+    uint64_t limit = 12 * F;
+    bool cut = false;
+    uint64_t cut_p = 0;
+    if (n_nodes + total >= budget) {
+        // first chunk-local parent p with n_nodes + #winners(parents <= p) >= budget (monotone in p)
+        uint64_t lo = 0, hi = F - 1;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (n_nodes + bm_rank(S.bitmap_global, S.prefix_global, (mid + 1) * 12) >= budget) hi = mid;
+            else lo = mid + 1;
+        }
+        cut = true;
+        cut_p = lo;
+        if (12 * (cut_p + 1) < limit) limit = 12 * (cut_p + 1);
+    }
+    const unsigned long long sol = red[kCtrlSol], err = red[kCtrlErr];
+    const int ierr = (int)red[kCtrlIerr];  // replicated: what every rank reported with this chunk's exchange
+    bool sol_here = false;
+    int status = 0;
+    if (sol != ~0ull && sol - 12 * head < limit) {  // solved at or before the cut parent
+        limit = sol - 12 * head;
+        sol_here = true;
+        cut = false;
+    }
+    if (err != ~0ull && (err >> 2) - 12 * head < limit) {  // the reference raises here, before anything later
+        limit = (err >> 2) - 12 * head;
+        status = (int)(err & 3);
+        sol_here = false;
+        cut = false;
+    }
+    // "New minimal length found" events in reference order
+    const uint64_t gid_limit = 12 * head + limit + (sol_here ? 1 : 0);
+    int min_len = st->min_len;
+    for (;;) {
+        unsigned long long best = ~0ull;
+        int bestL = -1;
+        for (int L = 0; L < min_len && L < 128; ++L) {
+            const unsigned long long g = red[kCtrlLen0 + L];
+            if (g < gid_limit && g < best) {
+                best = g;
+                bestL = L;
+            }
+        }
+        if (bestL < 0) break;
+        min_len = bestL;
+        if (st->n_minlen < 128) st->minlen_log[st->n_minlen++] = bestL;
+    }
+    st->min_len = min_len;
+    const uint64_t cg = bm_rank(S.bitmap_global, S.prefix_global, limit);
+    const uint64_t cl = bm_rank(bl, S.prefix_local, limit);
+    st->limit = (int64_t)limit;
+    st->head0 = st->head;
+    st->commit_pending = 1;
+    st->n_nodes0 = st->n_nodes;
+    st->n_local0 = st->n_local;
+    int my_ierr = ierr | st->ierr;
+    if ((uint64_t)st->n_local + cl > (uint64_t)st->cap_local) my_ierr |= IERR_SHARD_FULL;  // commit drops the excess
+    st->n_nodes += (int64_t)cg;
+    {
+        const uint64_t room_local = (uint64_t)st->cap_local - (uint64_t)st->n_local;
+        st->n_local += (int64_t)(cl < room_local ? cl : room_local);
+    }
+    if (sol_here) {
+        st->solved = 1;
+        st->sol_gid = (int64_t)sol;
+        st->n_expanded = (int64_t)(sol / 12 + 1);
+    } else if (status) {
+        st->status = status;
+        st->err_code = (int64_t)err;
+        st->n_expanded = (int64_t)((err >> 2) / 12 + 1);
+    } else if (cut) {
+        st->budget_hit = 1;
+        st->n_expanded = (int64_t)(head + cut_p + 1);
+    } else {
+        st->n_expanded = (int64_t)(head + F);
+    }
+    st->head += (int64_t)F;
+    st->chunks += 1;
+    st->epoch += 1;
+    st->buf ^= 1;
+    st->ierr = my_ierr;
+    // a rank-local error found after the exchange travels with the NEXT chunk's control block, so
+    // that every rank stops in the same chunk; errors seen by everyone stop the search now
+    const bool stop = st->solved || st->budget_hit || st->status || ierr || st->head >= st->n_nodes;
+    if (stop) {
+        st->done = 1;
+        return;
+    }
+    if (st->head == st->level_end) {
+        st->level_end = st->n_nodes;
+        st->levels += 1;
+    }
+    // chunk size: within the level, within the exchange buffers, and small enough that every
+    // rank's table stays <= 3/4 full even if all 12*F candidates were new (shares assumed <= 1.1/G + slack)
+    const int64_t G = st->world;
+    const int64_t est_local = G == 1 ? st->n_nodes : (int64_t)((double)st->n_nodes / (double)G * 1.1) + 100000;
+    const int64_t free_slots = (int64_t)(3 * ((st->tmask + 1) / 4)) - est_local;
+    int64_t room = G == 1 ? free_slots / 12 : (int64_t)((double)free_slots * (double)G / (12.0 * 1.15));
+    if (room < 1) room = 1;
+    int64_t Fn = st->level_end - st->head;
+    if (Fn > st->chunk_cap) Fn = st->chunk_cap;
+    if (Fn > room) Fn = room;
+    st->F = Fn;
+}
+
+// ---- commit ----------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
+    PbState* st = S.st;
+    // runs after decide of the same chunk: buf was flipped there, this chunk's buffers are buf^1.
+    // decide sets `done` for the LAST chunk too, whose winners must still be appended, so the
+    // commit is gated on the flag decide raises (prep of a later no-op chunk clears it).
+    if (!st->commit_pending) return;
+    const int buf = st->buf ^ 1;
+    __shared__ RegionMap R;
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int s = 0; s < S.world; ++s) {
+            R.start[s] = run;
+            unsigned long long n = __ldcg(&sh_ctrl(S, S.arena, buf, s)[kCtrlCount]);
+            if (n > (unsigned long long)st->pair_cap) n = (unsigned long long)st->pair_cap;
+            run += n;
+        }
+        for (int s = S.world; s <= kPbMaxWorld; ++s) R.start[s] = run;
+    }
+    __syncthreads();
+    const unsigned long long total = R.start[S.world];
+    const int64_t pair_cap = st->pair_cap;
+    const uint64_t* in_keys = sh_keys(S, S.arena, buf, pair_cap);
+    const uint32_t* in_c = sh_c(S, S.arena, buf, pair_cap);
+    const uint32_t* bl = sh_bitmap(S, S.arena, buf);
+    const uint64_t limit = (uint64_t)st->limit;
+    const uint64_t n_nodes0 = (uint64_t)st->n_nodes0, n_local0 = (uint64_t)st->n_local0;
+    const uint64_t head0 = (uint64_t)st->head0;
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+         v += (unsigned long long)gridDim.x * blockDim.x) {
+        const int64_t i = region_index(&R, S.world, pair_cap, v);
+        const uint32_t slot = S.rec_slot[i];
+        if (slot == kNoSlotPb) continue;
+        const uint64_t c = __ldcg(in_c + i);
+        if (c >= limit) continue;
+        if (!((S.bitmap_global[c >> 5] >> (c & 31)) & 1u)) continue;  // lost to an earlier candidate
+        const uint64_t g = n_nodes0 + bm_rank(S.bitmap_global, S.prefix_global, c);
+        const uint64_t idx = n_local0 + bm_rank(bl, S.prefix_local, c);
+        if (idx >= (uint64_t)st->cap_local) continue;  // IERR_SHARD_FULL was raised by decide
+        const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
+        store_key<W>(S.keys, idx, key);
+        S.parent[idx] = (int64_t)(((head0 + c / 12) << 4) | (c % 12));
+        S.gid[idx] = (int64_t)g;
+        const uint64_t h = pb_hash<W>(key);
+        S.table[slot] = ((h >> 41) << 40) | (idx + 1);
+    }
+}
+
+}  // namespace acs
+
+namespace acs {
+
+// one thread: smallest local index with gid >= value
+__device__ __forceinline__ int64_t pb_lower_bound(const int64_t* gid, int64_t n, int64_t value) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (gid[mid] < value) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// out = {found, parent gid, action, total length} of the node with global id `value`
+template <int W>
+__global__ void pb_lookup_kernel(const PbShard S, int64_t value, long long* out) {
+    const int64_t n = S.st->n_local;
+    const int64_t lo = pb_lower_bound(S.gid, n, value);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    if (lo < n && S.gid[lo] == value) {
+        const Key<W> k = load_key<W>(S.keys, (uint64_t)lo);
+        out[0] = 1;
+        out[1] = S.parent[lo] < 0 ? -1 : (S.parent[lo] >> 4);
+        out[2] = S.parent[lo] < 0 ? -1 : (S.parent[lo] & 15);
+        out[3] = (long long)(k.k[W - 1] >> 58) + (long long)(k.k[2 * W - 1] >> 58);
+    }
+}
+
+// all shards in this process: path of node `node` from the root, then (extra_action, extra_len)
+template <int W>
+__global__ void pb_path_kernel(const PbShard* shards, int n_shards, int64_t node, int extra_action, int extra_len,
+                               int32_t* path, int path_cap, int32_t* path_len) {
+    // pass 1: depth; pass 2: fill back to front
+    for (int pass = 0, depth = 0; pass < 2; ++pass) {
+        int pos = depth - 1, d = 0;
+        for (int64_t g = node; g >= 0;) {
+            int64_t par = -1;
+            int act = -1, L = 0;
+            for (int s = 0; s < n_shards; ++s) {
+                const PbShard& S = shards[s];
+                const int64_t n = S.st->n_local;
+                const int64_t lo = pb_lower_bound(S.gid, n, g);
+                if (lo < n && S.gid[lo] == g) {
+                    const Key<W> k = load_key<W>(S.keys, (uint64_t)lo);
+                    L = (int)(k.k[W - 1] >> 58) + (int)(k.k[2 * W - 1] >> 58);
+                    par = S.parent[lo] < 0 ? -1 : (S.parent[lo] >> 4);
+                    act = S.parent[lo] < 0 ? -1 : (int)(S.parent[lo] & 15);
+                    break;
+                }
+            }
+            if (pass == 1 && pos >= 0 && pos < path_cap) {
+                path[2 * pos] = act;
+                path[2 * pos + 1] = L;
+            }
+            --pos;
+            ++d;
+            g = par;
+        }
+        if (pass == 0) {
+            depth = d;
+            *path_len = depth + 1;
+            if (depth < path_cap) {
+                path[2 * depth] = extra_action;
+                path[2 * depth + 1] = extra_len;
+            }
+        }
+    }
+}
+
+}  // namespace acs
+
+// ---------------------------------------------------------------------------------------------
+using namespace acs;
+
+namespace {
+inline int pb_fail(int code, const std::string& m) {
+    acs::set_last_error(m.c_str());
+    return code;
+}
+#define PB_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            cudaGetLastError();                                                            \
+            return pb_fail(e__ == cudaErrorMemoryAllocation ? ACS_ERR_NOMEM : ACS_ERR_CUDA, \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));           \
+        }                                                                                  \
+    } while (0)
+inline int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
+constexpr int kRing = 4, kLag = 2;
+}  // namespace
+
+struct acs_pbfs {
+    int device = 0, rank = 0, world = 1, mrl = 0, W = 1, cyclical = 0;
+    int64_t budget = 0, cap_local = 0, chunk_cap = 0, pair_cap = 0;
+    uint64_t tcap = 0;
+    int64_t arena_bytes = 0;
+    PbShard S{};              // host copy of the pointer block (passed by value to the kernels)
+    PbShard* d_shards = nullptr;  // device array of all local shards (path kernel), owned by shard 0 of a local group
+    int n_group = 0;
+    void* ipc_opened[kPbMaxWorld] = {};
+    bool connected = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ring_ev[kRing] = {};
+    PbState* h_ring = nullptr;  // pinned [kRing]
+    PbState h_final{};
+    uint64_t epoch = 0;
+    int sms = 148;
+    int expand_wpb = 8, expand_blocks = 148;
+    size_t expand_smem = 0;
+    int32_t* d_path = nullptr;
+    int path_cap = 1 << 16;
+    long long* d_small = nullptr;
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+};
+
+extern "C" {
+
+int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes, int cyclical, int64_t chunk_parents,
+                    acs_pbfs** out) {
+    if (!out) return ACS_ERR_INVALID;
+    *out = nullptr;
+    if (mrl < 1 || mrl > 61) return pb_fail(ACS_ERR_UNSUPPORTED, "bfs needs 1 <= max_relator_length <= 61");
+    if (world < 1 || world > kPbMaxWorld || rank < 0 || rank >= world || max_nodes < 0)
+        return pb_fail(ACS_ERR_INVALID, "pbfs: bad rank / world / budget");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return pb_fail(ACS_ERR_NO_DEVICE, "no CUDA device visible; there is no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return pb_fail(ACS_ERR_INVALID, "pbfs: device index out of range");
+    PB_CUDA(cudaSetDevice(device));
+    acs_pbfs* b = new acs_pbfs();
+    b->device = device;
+    b->rank = rank;
+    b->world = world;
+    b->mrl = mrl;
+    b->W = mrl <= 29 ? 1 : 2;
+    b->cyclical = cyclical ? 1 : 0;
+    b->budget = max_nodes;
+    // hash partitioning is balanced to a few sigma of sqrt(n/world); the budget test overshoots by <= 11
+    b->cap_local = world == 1 ? max_nodes + 16 : (int64_t)((double)(max_nodes + 16) / world * 1.1) + 200000;
+    uint64_t t = 1024;
+    while (t < 2 * (uint64_t)b->cap_local) t <<= 1;
+    b->tcap = t;
+    auto bail = [&](int code, const std::string& m) {
+        acs_pbfs_destroy(b);
+        return pb_fail(code, m);
+    };
+    if (t > (1ull << 31)) return bail(ACS_ERR_UNSUPPORTED, "pbfs: more than 2^30 nodes per rank: use more GPUs");
+    // chunk size: per-rank work of ~4 Mi parents, bounded by the slot encodings (c < 2^30, record < 2^27)
+    int64_t chunk = chunk_parents > 0 ? chunk_parents : (int64_t)world << 22;
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(max_nodes + 16, 1024));
+    const int64_t rec_limit = (int64_t)1 << kRecBits;
+    auto pair_cap_of = [&](int64_t c) {
+        if (world == 1) return 12 * c;
+        return std::min<int64_t>(12 * c, (int64_t)((double)(12 * c) / ((double)world * world) * 1.3) + 16384);
+    };
+    while (chunk > 1024 && ((int64_t)world * pair_cap_of(chunk) > rec_limit || 12 * chunk >= ((int64_t)1 << kCBits))) chunk /= 2;
+    b->chunk_cap = chunk;
+    b->pair_cap = pair_cap_of(chunk);
+    if ((int64_t)world * b->pair_cap > rec_limit) return bail(ACS_ERR_UNSUPPORTED, "pbfs: exchange region too large");
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->sms = prop.multiProcessorCount;
+
+    PbShard& S = b->S;
+    S.W = b->W;
+    S.world = world;
+    S.rank = rank;
+    S.bitmap_words = (12 * chunk + 31) / 32 + 8;
+    S.nblk = (S.bitmap_words + kScanBlock - 1) / kScanBlock + 1;
+    int64_t off = 0;
+    S.off_flags = off;
+    off = align256(off + 2 * (int64_t)world * 8);
+    S.off_ctrl = off;
+    off = align256(off + 2 * (int64_t)world * kCtrlWords * 8);
+    S.off_bitmap = off;
+    off = align256(off + 2 * S.bitmap_words * 4);
+    S.off_keys = off;
+    off = align256(off + 2 * (int64_t)world * b->pair_cap * 16 * b->W);
+    S.off_c = off;
+    off = align256(off + 2 * (int64_t)world * b->pair_cap * 4);
+    b->arena_bytes = off;
+#define PB_ALLOC(ptr, bytes)                                                              \
+    do {                                                                                  \
+        cudaError_t e__ = cudaMalloc((void**)&(ptr), (size_t)(bytes));                    \
+        if (e__ != cudaSuccess) {                                                         \
+            cudaGetLastError();                                                           \
+            return bail(ACS_ERR_NOMEM, std::string("cudaMalloc(" #ptr "): ") + cudaGetErrorString(e__)); \
+        }                                                                                 \
+    } while (0)
+    PB_ALLOC(S.arena, b->arena_bytes);
+    PB_ALLOC(S.st, sizeof(PbState));
+    PB_ALLOC(S.keys, (size_t)b->cap_local * 16 * b->W);
+    PB_ALLOC(S.parent, (size_t)b->cap_local * 8);
+    PB_ALLOC(S.gid, (size_t)b->cap_local * 8);
+    PB_ALLOC(S.table, (size_t)b->tcap * 8);
+    PB_ALLOC(S.rec_slot, (size_t)world * b->pair_cap * 4);
+    PB_ALLOC(S.bitmap_global, (size_t)S.bitmap_words * 4);
+    PB_ALLOC(S.prefix_global, (size_t)(S.bitmap_words + 1) * 4);
+    PB_ALLOC(S.prefix_local, (size_t)(S.bitmap_words + 1) * 4);
+    PB_ALLOC(S.block_sums, (size_t)2 * S.nblk * 4);
+    PB_ALLOC(S.cursors, kPbMaxWorld * 8);
+    PB_ALLOC(S.ctrl_local, kCtrlWords * 8);
+    PB_ALLOC(b->d_path, (size_t)b->path_cap * 2 * sizeof(int32_t) + 16);
+    PB_ALLOC(b->d_small, 8 * sizeof(long long));
+#undef PB_ALLOC
+    // flags / control inboxes start at zero (epochs start at 1)
+    if (cudaMemset(S.arena, 0, (size_t)S.off_bitmap) != cudaSuccess) return bail(ACS_ERR_CUDA, "pbfs: memset(arena)");
+    if (cudaMallocHost((void**)&b->h_ring, kRing * sizeof(PbState)) != cudaSuccess)
+        return bail(ACS_ERR_NOMEM, "pbfs: cudaMallocHost");
+    if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(ACS_ERR_CUDA, "pbfs: cudaStreamCreate");
+    cudaEventCreate(&b->ev0);
+    cudaEventCreate(&b->ev1);
+    for (auto& e : b->ring_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    // expand launch shape: as many warps per block as ~100 KB of staging allows
+    const size_t per_warp = b->W == 1 ? queue_bytes_per_warp<1>(world) : queue_bytes_per_warp<2>(world);
+    int wpb = 8;
+    while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb /= 2;
+    b->expand_wpb = wpb;
+    b->expand_smem = per_warp * wpb;
+    cudaError_t e = cudaSuccess;
+    if (b->W == 1) {
+        e = cudaFuncSetAttribute(pb_expand_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->expand_smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(pb_expand_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->expand_smem);
+    } else {
+        e = cudaFuncSetAttribute(pb_expand_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->expand_smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(pb_expand_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->expand_smem);
+    }
+    if (e != cudaSuccess) return bail(ACS_ERR_CUDA, std::string("pbfs: expand smem attribute: ") + cudaGetErrorString(e));
+    int per_sm = 1;
+    if (b->W == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_expand_kernel<1, true>, 32 * wpb, b->expand_smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_expand_kernel<2, true>, 32 * wpb, b->expand_smem);
+    b->expand_blocks = b->sms * std::max(per_sm, 1);
+    for (int r = 0; r < kPbMaxWorld; ++r) S.peer[r] = nullptr;
+    S.peer[rank] = S.arena;
+    b->connected = world == 1;
+    *out = b;
+    return ACS_OK;
+}
+
+void acs_pbfs_destroy(acs_pbfs* b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    if (b->stream) {
+        cudaStreamSynchronize(b->stream);
+        cudaStreamDestroy(b->stream);
+    }
+    for (auto p : b->ipc_opened)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    for (auto e : b->ring_ev)
+        if (e) cudaEventDestroy(e);
+    PbShard& S = b->S;
+    cudaFree(S.arena);
+    cudaFree(S.st);
+    cudaFree(S.keys);
+    cudaFree(S.parent);
+    cudaFree(S.gid);
+    cudaFree(S.table);
+    cudaFree(S.rec_slot);
+    cudaFree(S.bitmap_global);
+    cudaFree(S.prefix_global);
+    cudaFree(S.prefix_local);
+    cudaFree(S.block_sums);
+    cudaFree(S.cursors);
+    cudaFree(S.ctrl_local);
+    cudaFree(b->d_path);
+    cudaFree(b->d_small);
+    cudaFree(b->d_shards);
+    if (b->h_ring) cudaFreeHost(b->h_ring);
+    cudaGetLastError();
+    delete b;
+}
+
+/* 64-byte cudaIpcMemHandle_t of this rank's exchange arena (inboxes, control inboxes, flags, bitmaps) */
+int acs_pbfs_export(acs_pbfs* b, void* handle64) {
+    if (!b || !handle64) return ACS_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    PB_CUDA(cudaSetDevice(b->device));
+    cudaIpcMemHandle_t h;
+    PB_CUDA(cudaIpcGetMemHandle(&h, b->S.arena));
+    std::memcpy(handle64, &h, 64);
+    return ACS_OK;
+}
+
+/* handles: world x 64 bytes in rank order (as gathered from acs_pbfs_export on every rank) */
+int acs_pbfs_connect(acs_pbfs* b, const void* handles) {
+    if (!b || !handles) return ACS_ERR_INVALID;
+    PB_CUDA(cudaSetDevice(b->device));
+    for (int r = 0; r < b->world; ++r) {
+        if (r == b->rank) continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, static_cast<const char*>(handles) + 64 * r, 64);
+        void* p = nullptr;
+        PB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        b->ipc_opened[r] = p;
+        b->S.peer[r] = static_cast<char*>(p);
+    }
+    b->connected = true;
+    return ACS_OK;
+}
+
+/* every rank of the world lives in this process (tests; single-process multi-GPU) */
+int acs_pbfs_connect_local(acs_pbfs** shards, int n) {
+    if (!shards || n < 1) return ACS_ERR_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (!shards[i] || shards[i]->world != n || shards[i]->rank != i) return pb_fail(ACS_ERR_INVALID, "pbfs: shards must be ranks 0..n-1 of a world of n");
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) {
+            shards[i]->S.peer[j] = shards[j]->S.arena;
+            if (shards[i]->device != shards[j]->device) {
+                PB_CUDA(cudaSetDevice(shards[i]->device));
+                int can = 0;
+                PB_CUDA(cudaDeviceCanAccessPeer(&can, shards[i]->device, shards[j]->device));
+                if (!can) return pb_fail(ACS_ERR_UNSUPPORTED, "pbfs: no peer access between the devices");
+                cudaError_t e = cudaDeviceEnablePeerAccess(shards[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PB_CUDA(e);
+                cudaGetLastError();
+            }
+        }
+        shards[i]->connected = true;
+    }
+    // device array of the pointer blocks for the path kernel
+    acs_pbfs* b0 = shards[0];
+    PB_CUDA(cudaSetDevice(b0->device));
+    if (b0->d_shards) cudaFree(b0->d_shards);
+    b0->d_shards = nullptr;
+    PB_CUDA(cudaMalloc((void**)&b0->d_shards, n * sizeof(PbShard)));
+    for (int i = 0; i < n; ++i)
+        PB_CUDA(cudaMemcpy(b0->d_shards + i, &shards[i]->S, sizeof(PbShard), cudaMemcpyHostToDevice));
+    b0->n_group = n;
+    return ACS_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <int W>
+int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_t* h_path, int path_cap,
+                acs_search_result* res) {
+    std::memset(res, 0, sizeof(*res));
+    acs_pbfs* b0 = sh[0];
+    const int world = b0->world;
+    Key<W> root;
+    int lens[2];
+    bool valid;
+    if (!pack_root<W>(h_presentation, b0->mrl, root, lens, valid))
+        return pb_fail(ACS_ERR_UNSUPPORTED, "bfs: letters outside {+-1,+-2} are not supported by the packed search");
+    if (!valid) {  // breadth_first.py:36-38 asserts is_array_valid_presentation
+        res->status = ACS_ROW_ASSERT;
+        return ACS_OK;
+    }
+    const uint64_t h = pb_hash<W>(root);
+    const int owner = world > 1 ? pb_owner(h, world) : 0;
+    bool same_device = true;
+    for (int i = 0; i < n_local; ++i) same_device = same_device && sh[i]->device == b0->device;
+    auto stream_of = [&](acs_pbfs* b) { return same_device ? b0->stream : b->stream; };
+
+    for (int i = 0; i < n_local; ++i) {
+        acs_pbfs* b = sh[i];
+        if (!b->connected) return pb_fail(ACS_ERR_INVALID, "pbfs: shard is not connected to its peers");
+        PB_CUDA(cudaSetDevice(b->device));
+        cudaStream_t s = stream_of(b);
+        PB_CUDA(cudaMemsetAsync(b->S.table, 0, b->tcap * sizeof(uint64_t), s));
+        PbState st{};
+        st.budget = b->budget;
+        st.cap_local = b->cap_local;
+        st.chunk_cap = b->chunk_cap;
+        st.pair_cap = b->pair_cap;
+        st.tmask = b->tcap - 1;
+        st.mrl = b->mrl;
+        st.cyclical = b->cyclical;
+        st.world = world;
+        st.rank = b->rank;
+        st.head = 0;
+        st.F = 1;
+        st.n_nodes = 1;
+        st.n_local = b->rank == owner ? 1 : 0;
+        st.level_end = 1;
+        st.epoch = b->epoch;
+        st.buf = (int)(b->epoch & 1);
+        st.min_len = lens[0] + lens[1];
+        st.sol_gid = -1;
+        b->h_ring[0] = st;  // pinned staging for the async upload
+        PB_CUDA(cudaMemcpyAsync(b->S.st, &b->h_ring[0], sizeof(PbState), cudaMemcpyHostToDevice, s));
+        if (b->rank == owner) {
+            const uint64_t slot_val = ((h >> 41) << 40) | 1ull;  // node index 0, stored +1
+            const int64_t none = -1, zero = 0;
+            PB_CUDA(cudaMemcpyAsync(b->S.keys, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+            PB_CUDA(cudaMemcpyAsync(b->S.parent, &none, 8, cudaMemcpyHostToDevice, s));
+            PB_CUDA(cudaMemcpyAsync(b->S.gid, &zero, 8, cudaMemcpyHostToDevice, s));
+            // first slot of the key's 4-slot bucket: where the insert kernel's probe sequence starts
+            PB_CUDA(cudaMemcpyAsync(b->S.table + ((h & (b->tcap - 1)) & ~3ull), &slot_val, 8, cudaMemcpyHostToDevice, s));
+        }
+        PB_CUDA(cudaStreamSynchronize(s));  // the staging copies above read host stack memory
+    }
+    PB_CUDA(cudaSetDevice(b0->device));
+    PB_CUDA(cudaEventRecord(b0->ev0, stream_of(b0)));
+
+    auto each = [&](auto&& fn) -> int {
+        for (int i = 0; i < n_local; ++i) {
+            acs_pbfs* b = sh[i];
+            if (!same_device) {
+                cudaError_t e = cudaSetDevice(b->device);
+                if (e != cudaSuccess) return pb_fail(ACS_ERR_CUDA, cudaGetErrorString(e));
+            }
+            fn(b, stream_of(b));
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return pb_fail(ACS_ERR_CUDA, std::string("pbfs launch: ") + cudaGetErrorString(e));
+        return ACS_OK;
+    };
+    const int wide = b0->sms * 8;
+    int rc = ACS_OK;
+    for (int64_t chunk = 0;; ++chunk) {
+        if (chunk >= kLag) {
+            PB_CUDA(cudaEventSynchronize(b0->ring_ev[(chunk - kLag) % kRing]));
+            if (b0->h_ring[(chunk - kLag) % kRing].done) break;
+        }
+#define PB_PHASE(expr)                                       \
+    rc = each([&](acs_pbfs* b, cudaStream_t s) { expr; });   \
+    if (rc != ACS_OK) return rc;
+        PB_PHASE((pb_prep_kernel<<<b->sms * 2, 256, 0, s>>>(b->S)));
+        if (chunk == 0) {
+            PB_PHASE((pb_expand_kernel<W, false><<<b->expand_blocks, 32 * b->expand_wpb, b->expand_smem, s>>>(b->S, b->expand_wpb)));
+        } else {
+            PB_PHASE((pb_expand_kernel<W, true><<<b->expand_blocks, 32 * b->expand_wpb, b->expand_smem, s>>>(b->S, b->expand_wpb)));
+        }
+        PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 0)));
+        if (world > 1) { PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 0, b->timeout_ns))); }
+        PB_PHASE((pb_insert_kernel<W><<<wide, 256, 0, s>>>(b->S)));
+        if (world > 1) {
+            PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 1)));
+            PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 1, b->timeout_ns)));
+        }
+        PB_PHASE((pb_scan_sums_kernel<<<b->sms * 4, kScanT, 0, s>>>(b->S)));
+        PB_PHASE((pb_scan_top_kernel<<<1, kScanT, 0, s>>>(b->S)));
+        PB_PHASE((pb_scan_final_kernel<<<b->sms * 4, kScanT, 0, s>>>(b->S)));
+        PB_PHASE((pb_decide_kernel<<<1, kCtrlWords, 0, s>>>(b->S)));
+        PB_PHASE((pb_commit_kernel<W><<<wide, 256, 0, s>>>(b->S)));
+#undef PB_PHASE
+        if (!same_device) PB_CUDA(cudaSetDevice(b0->device));
+        PB_CUDA(cudaMemcpyAsync(&b0->h_ring[chunk % kRing], b0->S.st, sizeof(PbState), cudaMemcpyDeviceToHost, stream_of(b0)));
+        PB_CUDA(cudaEventRecord(b0->ring_ev[chunk % kRing], stream_of(b0)));
+    }
+    PB_CUDA(cudaEventRecord(b0->ev1, stream_of(b0)));
+    int ierr = 0;
+    for (int i = 0; i < n_local; ++i) {
+        acs_pbfs* b = sh[i];
+        PB_CUDA(cudaSetDevice(b->device));
+        PB_CUDA(cudaStreamSynchronize(stream_of(b)));
+        PB_CUDA(cudaMemcpy(&b->h_final, b->S.st, sizeof(PbState), cudaMemcpyDeviceToHost));
+        b->epoch = b->h_final.epoch;
+        ierr |= b->h_final.ierr;
+    }
+    PB_CUDA(cudaSetDevice(b0->device));
+    const PbState& f = b0->h_final;
+    if (ierr) {
+        std::string m = "pbfs: internal error:";
+        if (ierr & IERR_PAIR_OVERFLOW) m += " exchange region overflow (skewed partition; pass a smaller chunk)";
+        if (ierr & IERR_TABLE_FULL) m += " visited table full";
+        if (ierr & IERR_SHARD_FULL) m += " shard capacity exceeded (skewed partition)";
+        if (ierr & IERR_TIMEOUT) m += " timed out waiting for a peer rank";
+        return pb_fail(ACS_ERR_CUDA, m);
+    }
+    res->solved = f.solved;
+    res->status = f.status;
+    res->budget_hit = f.budget_hit;
+    res->n_visited = f.n_nodes;
+    res->n_expanded = f.n_expanded;
+    res->n_moves = f.solved ? f.sol_gid + 1 : (f.status ? (int64_t)(((uint64_t)f.err_code >> 2) + 1) : f.n_expanded * 12);
+    res->frontier_left = f.n_nodes - f.n_expanded;
+    res->n_levels = f.levels;
+    res->n_minlen = f.n_minlen;
+    for (int i = 0; i < f.n_minlen && i < 128; ++i) res->minlen_log[i] = f.minlen_log[i];
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, b0->ev0, b0->ev1);
+    res->seconds_device = ms * 1e-3;
+    if (f.solved && n_local == world && b0->d_shards && b0->n_group == world) {
+        const int cap = std::min(path_cap, b0->path_cap);
+        int32_t* d_len = b0->d_path + 2 * (size_t)b0->path_cap;
+        cudaStream_t s = stream_of(b0);
+        pb_path_kernel<W><<<1, 1, 0, s>>>(b0->d_shards, world, f.sol_gid / 12, (int)(f.sol_gid % 12), 2, b0->d_path, cap, d_len);
+        PB_CUDA(cudaGetLastError());
+        int32_t plen = 0;
+        PB_CUDA(cudaMemcpyAsync(&plen, d_len, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaStreamSynchronize(s));
+        res->path_len = plen;
+        if (h_path && cap > 0)
+            PB_CUDA(cudaMemcpy(h_path, b0->d_path, (size_t)std::min(plen, cap) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return ACS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* Runs the search on the local shards (all `world` ranks of a single-process world, or this
+ * process's one rank of a multi-process world: every process calls it with the same arguments).
+ * The path is produced here only when all ranks are local; otherwise walk it with
+ * acs_pbfs_lookup (see ac_solver_b200/search/partitioned.py). */
+int acs_pbfs_run(acs_pbfs** shards, int n_local, const int8_t* h_presentation, int32_t* h_path, int path_cap,
+                 acs_search_result* res) {
+    if (!shards || n_local < 1 || !shards[0] || !h_presentation || !res) return ACS_ERR_INVALID;
+    for (int i = 0; i < n_local; ++i)
+        if (!shards[i] || shards[i]->W != shards[0]->W || shards[i]->world != shards[0]->world) return ACS_ERR_INVALID;
+    if (n_local != 1 && n_local != shards[0]->world) return pb_fail(ACS_ERR_INVALID, "pbfs: pass one shard or all of them");
+    return shards[0]->W == 1 ? pb_run_impl<1>(shards, n_local, h_presentation, h_path, path_cap, res)
+                             : pb_run_impl<2>(shards, n_local, h_presentation, h_path, path_cap, res);
+}
+
+/* out4 = {found on this rank, parent global id (-1 root), action (-1 root), total length} */
+int acs_pbfs_lookup(acs_pbfs* b, int64_t gid, int64_t* out4) {
+    if (!b || !out4) return ACS_ERR_INVALID;
+    PB_CUDA(cudaSetDevice(b->device));
+    if (b->W == 1) pb_lookup_kernel<1><<<1, 1, 0, b->stream>>>(b->S, gid, b->d_small);
+    else pb_lookup_kernel<2><<<1, 1, 0, b->stream>>>(b->S, gid, b->d_small);
+    PB_CUDA(cudaGetLastError());
+    PB_CUDA(cudaMemcpyAsync(out4, b->d_small, 4 * sizeof(long long), cudaMemcpyDeviceToHost, b->stream));
+    PB_CUDA(cudaStreamSynchronize(b->stream));
+    return ACS_OK;
+}
+
+/* this rank's visited states (int8 rows) and their global ids (= FIFO positions), local order */
+int acs_pbfs_visited(acs_pbfs* b, int64_t* h_gid, int8_t* h_rows, int64_t cap_rows, int64_t* n_out) {
+    if (!b || (cap_rows > 0 && (!h_gid || !h_rows))) return ACS_ERR_INVALID;
+    PB_CUDA(cudaSetDevice(b->device));
+    const int64_t n = std::min<int64_t>(b->h_final.n_local, std::max<int64_t>(cap_rows, 0));
+    if (n_out) *n_out = n;
+    if (n == 0) return ACS_OK;
+    int8_t* d = nullptr;
+    PB_CUDA(cudaMalloc((void**)&d, (size_t)n * 2 * b->mrl));
+    if (b->W == 1) keys_unpack_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->S.keys, d, (uint64_t)n, b->mrl);
+    else keys_unpack_kernel<2><<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->S.keys, d, (uint64_t)n, b->mrl);
+    cudaError_t e = cudaMemcpyAsync(h_rows, d, (size_t)n * 2 * b->mrl, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_gid, b->S.gid, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(d);
+    PB_CUDA(e);
+    return ACS_OK;
+}
+
+/* counters of the last run on this rank: {n_local, chunks, records sent, records received, chunk_cap, pair_cap,
+ * arena bytes, table slots} */
+int acs_pbfs_stats(acs_pbfs* b, int64_t* out8) {
+    if (!b || !out8) return ACS_ERR_INVALID;
+    out8[0] = b->h_final.n_local;
+    out8[1] = b->h_final.chunks;
+    out8[2] = (int64_t)b->h_final.records_sent;
+    out8[3] = (int64_t)b->h_final.records_recv;
+    out8[4] = b->chunk_cap;
+    out8[5] = b->pair_cap;
+    out8[6] = b->arena_bytes;
+    out8[7] = (int64_t)b->tcap;
+    return ACS_OK;
+}
+
+int acs_pbfs_set_timeout(acs_pbfs* b, double seconds) {
+    if (!b || seconds <= 0) return ACS_ERR_INVALID;
+    b->timeout_ns = (unsigned long long)(seconds * 1e9);
+    return ACS_OK;
+}
+
+}  // extern "C"

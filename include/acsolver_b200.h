@@ -217,6 +217,36 @@ int acs_sbfs_lower_bound(const int64_t *d_gid, int64_t n, int64_t value, int64_t
 int acs_sbfs_lookup(const acs_sbfs_args *a, int64_t gid, int64_t *d_out4, void *stream);
 int acs_sbfs_unpack(const uint64_t *d_keys, int8_t *d_out, int64_t n, int mrl, void *stream);
 
+/* ---- hash-partitioned BFS, native driver (csrc/pbfs.cu) ------------------------------------------
+ * Replaces search/breadth_first.py:15-97 for one GPU (world 1) and for a hash-partitioned search over
+ * the GPUs of one node (one process per GPU).  The chunk loop runs on the device streams with no host
+ * synchronisation; newly generated states go straight into the owner rank's inbox by peer stores over
+ * NVLink (the exchange arena is shared through cudaIpc handles), synchronised by release/acquire
+ * epoch flags in peer memory.  Same sequential contract and bit-identical results for every world
+ * size.  Usage, on every rank: create -> export -> (all-gather the 64-byte handles with any host
+ * channel, e.g. torch.distributed) -> connect -> run (same arguments on every rank) -> lookup /
+ * visited -> destroy.  For tests all ranks may live in one process: create world shards, then
+ * acs_pbfs_connect_local. */
+typedef struct acs_pbfs acs_pbfs;
+/* chunk_parents <= 0 picks the default (world * 4 Mi parents per chunk). */
+int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes, int cyclical,
+                    int64_t chunk_parents, acs_pbfs **out);
+int acs_pbfs_export(acs_pbfs *b, void *handle64);
+int acs_pbfs_connect(acs_pbfs *b, const void *handles /* world x 64 bytes, rank order */);
+int acs_pbfs_connect_local(acs_pbfs **shards, int n);
+/* shards: this process's one rank, or all ranks of a single-process world.  h_path (int32 pairs,
+ * capacity path_cap) is filled only when all ranks are local; otherwise use acs_pbfs_lookup. */
+int acs_pbfs_run(acs_pbfs **shards, int n_local, const int8_t *h_presentation, int32_t *h_path, int path_cap,
+                 acs_search_result *res);
+/* out4 = {found on this rank, parent global id (-1 root), action (-1 root), total length} */
+int acs_pbfs_lookup(acs_pbfs *b, int64_t gid, int64_t *out4);
+/* this rank's visited states and their global ids (= FIFO positions of the reference's tree_nodes) */
+int acs_pbfs_visited(acs_pbfs *b, int64_t *h_gid, int8_t *h_rows, int64_t cap_rows, int64_t *n_out);
+/* {n_local, chunks, records sent, records received, chunk_cap, pair_cap, arena bytes, table slots} */
+int acs_pbfs_stats(acs_pbfs *b, int64_t *out8);
+int acs_pbfs_set_timeout(acs_pbfs *b, double seconds);
+void acs_pbfs_destroy(acs_pbfs *b);
+
 #ifdef __cplusplus
 }
 #endif
