@@ -44,6 +44,8 @@
 // on one device (kernels of the shards are then serialised on one stream) or on several.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,21 +60,19 @@
 namespace acs {
 
 constexpr int kPbMaxWorld = 16;
-constexpr int kCtrlWords = 136;        // sol, err, first_len[128], count, ierr, pad
-constexpr int kCtrlSol = 0, kCtrlErr = 1, kCtrlLen0 = 2, kCtrlCount = 130, kCtrlIerr = 131;
-constexpr uint64_t kTent = 1ull << 63;  // tentative slot: bit 63 | c:30 << 33 | record:27 << 6 | fp:6
-constexpr int kCBits = 30, kRecBits = 27;
-constexpr uint64_t kCMask = (1ull << kCBits) - 1, kRecMask = (1ull << kRecBits) - 1;
-constexpr uint32_t kNoSlotPb = 0xFFFFFFFFu;
+constexpr int kCtrlWords = 136;        // sol, err, first_len[128], log end, ierr, log start, pad
+constexpr int kCtrlSol = 0, kCtrlErr = 1, kCtrlLen0 = 2, kCtrlCount = 130, kCtrlIerr = 131, kCtrlStart = 132;
+// table slot: 23-bit fingerprint << 40 | (record-log position + 1); 0 = empty
+constexpr uint64_t kPosMask = (1ull << 40) - 1;
 constexpr int kQueue = 64;              // per-warp, per-destination staging ring (records)
 constexpr int kScanT = 256, kScanPer = 8, kScanBlock = kScanT * kScanPer;  // words per scan block
 
-enum : int { IERR_PAIR_OVERFLOW = 1, IERR_TABLE_FULL = 2, IERR_SHARD_FULL = 4, IERR_TIMEOUT = 8 };
+enum : int { IERR_LOG_FULL = 1, IERR_TABLE_FULL = 2, IERR_SHARD_FULL = 4, IERR_TIMEOUT = 8 };
 
 // Device-resident run state of one rank.  Every scalar decision is replicated on all ranks.
 struct PbState {
     // constants of the run
-    int64_t budget, cap_local, chunk_cap, pair_cap;
+    int64_t budget, cap_local, chunk_cap, log_cap;
     uint64_t tmask;
     int32_t mrl, cyclical, world, rank;
     // current chunk
@@ -96,12 +96,12 @@ struct PbShard {
     int64_t* parent;     // [cap]
     int64_t* gid;        // [cap]
     uint64_t* table;     // [tmask+1]
-    uint32_t* rec_slot;  // [world*pair_cap]
     uint32_t* bitmap_global;
     uint32_t* prefix_global;  // [words+1]
     uint32_t* prefix_local;   // [words+1]
     uint32_t* block_sums;     // [2][nblk]
-    unsigned long long* cursors;     // [world]
+    unsigned long long* cursors;     // [world] append positions in the peers' record logs (persist over a run)
+    unsigned long long* cstart;      // [world] their values at the start of the current chunk
     unsigned long long* ctrl_local;  // [kCtrlWords]
     // arena (same layout on every rank)
     char* arena;                     // own
@@ -109,8 +109,8 @@ struct PbShard {
     int64_t off_flags;               // [2][world] u64
     int64_t off_ctrl;                // [2 buf][world][kCtrlWords] u64
     int64_t off_bitmap;              // [2 buf][bitmap_words] u32
-    int64_t off_keys;                // [2 buf][world][pair_cap][2W] u64
-    int64_t off_c;                   // [2 buf][world][pair_cap] u32
+    int64_t off_keys;                // [world src][log_cap][2W] u64   record log: state keys ...
+    int64_t off_c;                   // [world src][log_cap] u32        ... and candidate ids
     int64_t bitmap_words, nblk;
     int32_t W, world, rank, pad;
 };
@@ -170,11 +170,11 @@ __device__ __forceinline__ unsigned long long* sh_ctrl(const PbShard& S, char* b
 __device__ __forceinline__ uint32_t* sh_bitmap(const PbShard& S, char* base, int buf) {
     return reinterpret_cast<uint32_t*>(base + S.off_bitmap) + (int64_t)buf * S.bitmap_words;
 }
-__device__ __forceinline__ uint64_t* sh_keys(const PbShard& S, char* base, int buf, int64_t pair_cap) {
-    return reinterpret_cast<uint64_t*>(base + S.off_keys) + (int64_t)buf * S.world * pair_cap * 2 * S.W;
+__device__ __forceinline__ uint64_t* sh_keys(const PbShard& S, char* base) {
+    return reinterpret_cast<uint64_t*>(base + S.off_keys);
 }
-__device__ __forceinline__ uint32_t* sh_c(const PbShard& S, char* base, int buf, int64_t pair_cap) {
-    return reinterpret_cast<uint32_t*>(base + S.off_c) + (int64_t)buf * S.world * pair_cap;
+__device__ __forceinline__ uint32_t* sh_c(const PbShard& S, char* base) {
+    return reinterpret_cast<uint32_t*>(base + S.off_c);
 }
 
 // ---- prep ----------------------------------------------------------------------------------
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) pb_prep_kernel(const PbShard S) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x)
         bm[i] = 0;
     if (blockIdx.x != 0) return;
-    if (threadIdx.x < S.world) S.cursors[threadIdx.x] = 0;
+    if (threadIdx.x < S.world) S.cstart[threadIdx.x] = S.cursors[threadIdx.x];
     if (threadIdx.x < kCtrlWords)
         S.ctrl_local[threadIdx.x] = (threadIdx.x == kCtrlCount || threadIdx.x == kCtrlIerr) ? 0ull : ~0ull;
     if (threadIdx.x == 0) {
@@ -226,18 +226,18 @@ __device__ __forceinline__ void pb_flush(const PbShard& S, const PbState* st, Wa
     if (lane == 0) pos = atomicAdd(&S.cursors[d], (unsigned long long)n);
     pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
     const uint32_t hd = Q.head[d];
-    if (pos + n > (unsigned long long)st->pair_cap) {
-        if (lane == 0) atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_PAIR_OVERFLOW);
+    if (pos + n > (unsigned long long)st->log_cap) {
+        if (lane == 0) atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_LOG_FULL);
     } else if ((uint32_t)lane < n) {
         const uint32_t q = (hd + lane) & (kQueue - 1);
         char* base = S.peer[d];
-        const int64_t r = (int64_t)S.rank * st->pair_cap + (int64_t)pos + lane;
-        uint64_t* dk = sh_keys(S, base, st->buf, st->pair_cap) + r * 2 * W;
+        const int64_t r = (int64_t)S.rank * st->log_cap + (int64_t)pos + lane;
+        uint64_t* dk = sh_keys(S, base) + r * 2 * W;
         const uint64_t* sk = Q.keys + ((size_t)d * kQueue + q) * 2 * W;
 #pragma unroll
         for (int i = 0; i < W; ++i)
             reinterpret_cast<ulonglong2*>(dk)[i] = make_ulonglong2(sk[2 * i], sk[2 * i + 1]);
-        sh_c(S, base, st->buf, st->pair_cap)[r] = Q.c[d * kQueue + q];
+        sh_c(S, base)[r] = Q.c[d * kQueue + q];
     }
     __syncwarp();
     if (lane == 0) {
@@ -250,23 +250,33 @@ __device__ __forceinline__ void pb_flush(const PbShard& S, const PbState* st, Wa
 template <int W>
 __device__ __noinline__ void pb_enqueue(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int dest,
                                         const Key<W>& child, uint32_t c, int lane) {
-    const int world = S.world;
-    for (int d = 0; d < world; ++d) {
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, dest == d);
-        if (mask == 0) continue;
-        const uint32_t base = Q.cnt[d];
-        if (dest == d) {
-            const uint32_t q = (Q.head[d] + base + __popc(mask & ((1u << lane) - 1u))) & (kQueue - 1);
-            uint64_t* sk = Q.keys + ((size_t)d * kQueue + q) * 2 * W;
-#pragma unroll
-            for (int i = 0; i < 2 * W; ++i) sk[i] = child.k[i];
-            Q.c[d * kQueue + q] = c;
+    const uint32_t act = __ballot_sync(0xFFFFFFFFu, dest >= 0);
+    if (act == 0) return;
+    bool lead_full = false;
+    if (dest >= 0) {
+        // lanes with the same destination reserve consecutive ring positions through their leader
+        const uint32_t grp = __match_any_sync(act, dest);
+        const int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if (lane == leader) {
+            base = Q.cnt[dest];
+            Q.cnt[dest] = base + __popc(grp);
         }
-        __syncwarp();
-        const uint32_t total = base + __popc(mask);
-        if (lane == 0) Q.cnt[d] = total;
-        __syncwarp();
-        if (total >= 32) pb_flush<W>(S, st, Q, d, 32, lane);
+        base = __shfl_sync(grp, base, leader);
+        const uint32_t q = (Q.head[dest] + base + __popc(grp & ((1u << lane) - 1u))) & (kQueue - 1);
+        uint64_t* sk = Q.keys + ((size_t)dest * kQueue + q) * 2 * W;
+#pragma unroll
+        for (int i = 0; i < 2 * W; ++i) sk[i] = child.k[i];
+        Q.c[dest * kQueue + q] = c;
+        lead_full = lane == leader && base + __popc(grp) >= 32;
+    }
+    __syncwarp();
+    uint32_t fl = __ballot_sync(0xFFFFFFFFu, lead_full);
+    while (fl) {
+        const int l = __ffs(fl) - 1;
+        fl &= fl - 1;
+        const int d = __shfl_sync(0xFFFFFFFFu, dest, l);
+        pb_flush<W>(S, st, Q, d, 32, lane);
     }
 }
 
@@ -306,9 +316,15 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
 #pragma unroll
         for (int i = 0; i < 2 * W; ++i) pk.k[i] = 0;
         uint64_t pg = 0;
+        int back = -1;  // the move that undoes the one which created this node: its child is the node's own parent
         if (valid) {
             pk = load_key<W>(S.keys, (uint64_t)j);
             pg = (uint64_t)S.gid[j];
+            if (TRUSTED && !cyc) {
+                const int64_t pl = S.parent[j];
+                // inverse pairs: r1<-r1 r0 / r1<-r1 r0^-1 (0,2); r0<-r0 r1^-1 / r0<-r0 r1 (1,3); conjugation by g / g^-1
+                if (pl >= 0) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
+            }
         }
         Rel<2 * W> p0, p1;
         split_key<W>(pk, p0, p1);
@@ -320,7 +336,7 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
             Key<W> child;
 #pragma unroll
             for (int i = 0; i < 2 * W; ++i) child.k[i] = 0;
-            if (valid) {
+            if (valid && a != back) {
                 bool co;
                 const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
                 const uint64_t gidc = pg * 12 + a;
@@ -363,6 +379,7 @@ __global__ void __launch_bounds__(256) pb_signal_kernel(const PbShard S, int kin
             const int d = i / kCtrlWords, w = i % kCtrlWords;
             unsigned long long v = S.ctrl_local[w];
             if (w == kCtrlCount) v = S.cursors[d];
+            if (w == kCtrlStart) v = S.cstart[d];
             if (w == kCtrlIerr) v |= (unsigned long long)st->ierr;
             sh_ctrl(S, S.peer[d], st->buf, S.rank)[w] = v;
         }
@@ -390,28 +407,40 @@ __global__ void __launch_bounds__(32) pb_wait_kernel(const PbShard S, int kind, 
 }
 
 // ---- insert ----------------------------------------------------------------------------------
+// The records of a chunk are the tails [start, end) of the per-source record logs.
 struct RegionMap {
-    unsigned long long start[kPbMaxWorld + 1];  // prefix of the per-source record counts
+    unsigned long long vstart[kPbMaxWorld + 1];  // prefix of the per-source record counts of this chunk
+    unsigned long long cstart[kPbMaxWorld];      // log offset of each source's first record of this chunk
 };
-__device__ __forceinline__ void load_regions(const PbShard& S, const PbState* st, RegionMap* R) {
+__device__ __forceinline__ void load_regions(const PbShard& S, const PbState* st, int buf, RegionMap* R) {
     if (threadIdx.x == 0) {
         unsigned long long run = 0;
         for (int s = 0; s < S.world; ++s) {
-            R->start[s] = run;
-            unsigned long long n = __ldcg(&sh_ctrl(S, S.arena, st->buf, s)[kCtrlCount]);
-            if (n > (unsigned long long)st->pair_cap) n = (unsigned long long)st->pair_cap;  // overflow is flagged by the sender
-            run += n;
+            const unsigned long long* ctrl = sh_ctrl(S, S.arena, buf, s);
+            unsigned long long lo = __ldcg(&ctrl[kCtrlStart]), hi = __ldcg(&ctrl[kCtrlCount]);
+            if (hi > (unsigned long long)st->log_cap) hi = (unsigned long long)st->log_cap;  // overflow is flagged by the sender
+            if (lo > hi) lo = hi;
+            R->vstart[s] = run;
+            R->cstart[s] = lo;
+            run += hi - lo;
         }
-        for (int s = S.world; s <= kPbMaxWorld; ++s) R->start[s] = run;
+        for (int s = S.world; s <= kPbMaxWorld; ++s) R->vstart[s] = run;
     }
     __syncthreads();
 }
-// virtual record index v (0 <= v < total) -> flat inbox index src*pair_cap + offset
-__device__ __forceinline__ int64_t region_index(const RegionMap* R, int world, int64_t pair_cap, unsigned long long v) {
+// virtual record index v (0 <= v < total) -> position in this rank's record log
+__device__ __forceinline__ int64_t region_index(const RegionMap* R, int world, int64_t log_cap, unsigned long long v) {
     int s = 0;
 #pragma unroll 1
-    for (int k = 1; k < world; ++k) s += (v >= R->start[k]) ? 1 : 0;
-    return (int64_t)s * pair_cap + (int64_t)(v - R->start[s]);
+    for (int k = 1; k < world; ++k) s += (v >= R->vstart[k]) ? 1 : 0;
+    return (int64_t)s * log_cap + (int64_t)(R->cstart[s] + (v - R->vstart[s]));
+}
+// does log position p belong to the current chunk (a tentative entry)?
+__device__ __forceinline__ bool is_tentative(const RegionMap* R, int world, int64_t log_cap, uint64_t p) {
+    int s = 0;
+#pragma unroll 1
+    for (int k = 1; k < world; ++k) s += (p >= (uint64_t)k * (uint64_t)log_cap) ? 1 : 0;
+    return p - (uint64_t)s * (uint64_t)log_cap >= R->cstart[s];
 }
 
 template <int W>
@@ -419,24 +448,23 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
     PbState* st = S.st;
     if (st->done) return;
     __shared__ RegionMap R;
-    load_regions(S, st, &R);
-    const unsigned long long total = R.start[S.world];
-    const int64_t pair_cap = st->pair_cap;
-    const uint64_t* in_keys = sh_keys(S, S.arena, st->buf, pair_cap);
-    const uint32_t* in_c = sh_c(S, S.arena, st->buf, pair_cap);
+    load_regions(S, st, st->buf, &R);
+    const unsigned long long total = R.vstart[S.world];
+    const int64_t log_cap = st->log_cap;
+    const uint64_t* in_keys = sh_keys(S, S.arena);
+    const uint32_t* in_c = sh_c(S, S.arena);
     uint32_t* bm = sh_bitmap(S, S.arena, st->buf);
     const uint64_t tmask = st->tmask;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->records_recv += total;
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
          v += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t i = region_index(&R, S.world, pair_cap, v);
+        const int64_t i = region_index(&R, S.world, log_cap, v);
         const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
         const uint32_t c = __ldcg(in_c + i);
         const uint64_t h = pb_hash<W>(key);
-        const uint64_t fp23 = h >> 41, fp6 = h >> 58;
-        const uint64_t mine = kTent | ((uint64_t)c << 33) | ((uint64_t)i << 6) | fp6;
+        const uint64_t fp23 = h >> 41;
+        const uint64_t mine = (fp23 << 40) | ((uint64_t)i + 1);
         uint64_t s = (h & tmask) & ~3ull;
-        uint32_t my_slot = kNoSlotPb;
         uint64_t probes = 0;
         bool finished = false;
         while (!finished) {
@@ -446,34 +474,36 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
 #pragma unroll
             for (int jj = 0; jj < 4 && !finished; ++jj) {
                 uint64_t cur = vv[jj];
-                const uint64_t slot = s + jj;
+                unsigned long long* slot = (unsigned long long*)&S.table[s + jj];
                 if (cur == 0) {
-                    cur = atomicCAS((unsigned long long*)&S.table[slot], 0ull, (unsigned long long)mine);
-                    if (cur == 0) {
-                        my_slot = (uint32_t)slot;
+                    cur = atomicCAS(slot, 0ull, (unsigned long long)mine);
+                    if (cur == 0) {  // first sighting of this state: claim
                         atomicXor(&bm[c >> 5], 1u << (c & 31));
                         finished = true;
                         break;
                     }
                 }
-                if (!(cur & kTent)) {  // committed node
-                    if ((cur >> 40) == fp23) {
-                        const Key<W> other = load_key<W>(S.keys, (cur & kIdxMask) - 1);
-                        if (key_eq<W>(other, key)) finished = true;  // already visited
-                    }
-                } else if ((cur & 63ull) == fp6) {  // tentative record of this chunk
-                    const Key<W> other = load_key_cg<W>(in_keys, (cur >> 6) & kRecMask);
-                    if (key_eq<W>(other, key)) {
-                        const uint64_t old = atomicMin((unsigned long long*)&S.table[slot], (unsigned long long)mine);
-                        if (old > mine) {  // this record displaced `old` (same key, larger candidate id)
-                            const uint32_t co = (uint32_t)((old >> 33) & kCMask);
-                            atomicXor(&bm[co >> 5], 1u << (co & 31));
+                if ((cur >> 40) != fp23) continue;
+                uint64_t p2 = (cur & kPosMask) - 1;
+                const Key<W> other = load_key_cg<W>(in_keys, p2);
+                if (!key_eq<W>(other, key)) continue;
+                // the same state: an older chunk's record (visited), or a record of this chunk --
+                // then the smaller candidate id keeps the slot (FIFO order of the reference)
+                if (is_tentative(&R, S.world, log_cap, p2)) {
+                    for (;;) {
+                        const uint32_t c2 = __ldcg(in_c + p2);
+                        if (c2 < c) break;
+                        const uint64_t old = atomicCAS(slot, (unsigned long long)cur, (unsigned long long)mine);
+                        if (old == cur) {  // displaced the holder: its claim bit flips back, mine flips on
+                            atomicXor(&bm[c2 >> 5], 1u << (c2 & 31));
                             atomicXor(&bm[c >> 5], 1u << (c & 31));
-                            my_slot = (uint32_t)slot;
+                            break;
                         }
-                        finished = true;
+                        cur = old;  // someone else replaced it meanwhile (same state): look again
+                        p2 = (cur & kPosMask) - 1;
                     }
                 }
+                finished = true;
             }
             if (!finished) {
                 s = (s + 4) & tmask;
@@ -484,7 +514,6 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
                 }
             }
         }
-        S.rec_slot[i] = my_slot;
     }
 }
 
@@ -764,42 +793,27 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
     if (!st->commit_pending) return;
     const int buf = st->buf ^ 1;
     __shared__ RegionMap R;
-    if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int s = 0; s < S.world; ++s) {
-            R.start[s] = run;
-            unsigned long long n = __ldcg(&sh_ctrl(S, S.arena, buf, s)[kCtrlCount]);
-            if (n > (unsigned long long)st->pair_cap) n = (unsigned long long)st->pair_cap;
-            run += n;
-        }
-        for (int s = S.world; s <= kPbMaxWorld; ++s) R.start[s] = run;
-    }
-    __syncthreads();
-    const unsigned long long total = R.start[S.world];
-    const int64_t pair_cap = st->pair_cap;
-    const uint64_t* in_keys = sh_keys(S, S.arena, buf, pair_cap);
-    const uint32_t* in_c = sh_c(S, S.arena, buf, pair_cap);
+    load_regions(S, st, buf, &R);
+    const unsigned long long total = R.vstart[S.world];
+    const int64_t log_cap = st->log_cap;
+    const uint64_t* in_keys = sh_keys(S, S.arena);
+    const uint32_t* in_c = sh_c(S, S.arena);
     const uint32_t* bl = sh_bitmap(S, S.arena, buf);
     const uint64_t limit = (uint64_t)st->limit;
     const uint64_t n_nodes0 = (uint64_t)st->n_nodes0, n_local0 = (uint64_t)st->n_local0;
     const uint64_t head0 = (uint64_t)st->head0;
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
          v += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t i = region_index(&R, S.world, pair_cap, v);
-        const uint32_t slot = S.rec_slot[i];
-        if (slot == kNoSlotPb) continue;
+        const int64_t i = region_index(&R, S.world, log_cap, v);
         const uint64_t c = __ldcg(in_c + i);
         if (c >= limit) continue;
-        if (!((S.bitmap_global[c >> 5] >> (c & 31)) & 1u)) continue;  // lost to an earlier candidate
+        if (!((__ldcg(bl + (c >> 5)) >> (c & 31)) & 1u)) continue;  // an already visited state, or lost to an earlier candidate
         const uint64_t g = n_nodes0 + bm_rank(S.bitmap_global, S.prefix_global, c);
         const uint64_t idx = n_local0 + bm_rank(bl, S.prefix_local, c);
         if (idx >= (uint64_t)st->cap_local) continue;  // IERR_SHARD_FULL was raised by decide
-        const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
-        store_key<W>(S.keys, idx, key);
+        store_key<W>(S.keys, idx, load_key_cg<W>(in_keys, (uint64_t)i));
         S.parent[idx] = (int64_t)(((head0 + c / 12) << 4) | (c % 12));
         S.gid[idx] = (int64_t)g;
-        const uint64_t h = pb_hash<W>(key);
-        S.table[slot] = ((h >> 41) << 40) | (idx + 1);
     }
 }
 
@@ -899,7 +913,7 @@ constexpr int kRing = 4, kLag = 2;
 
 struct acs_pbfs {
     int device = 0, rank = 0, world = 1, mrl = 0, W = 1, cyclical = 0;
-    int64_t budget = 0, cap_local = 0, chunk_cap = 0, pair_cap = 0;
+    int64_t budget = 0, cap_local = 0, chunk_cap = 0, log_cap = 0;
     uint64_t tcap = 0;
     int64_t arena_bytes = 0;
     PbShard S{};              // host copy of the pointer block (passed by value to the kernels)
@@ -955,20 +969,25 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
         return pb_fail(code, m);
     };
     if (t > (1ull << 31)) return bail(ACS_ERR_UNSUPPORTED, "pbfs: more than 2^30 nodes per rank: use more GPUs");
-    // chunk size: per-rank work of ~4 Mi parents, bounded by the slot encodings (c < 2^30, record < 2^27)
+    // chunk size: per-rank work of ~4 Mi parents; candidate ids are 32-bit
     int64_t chunk = chunk_parents > 0 ? chunk_parents : (int64_t)world << 22;
     chunk = std::min<int64_t>(chunk, std::max<int64_t>(max_nodes + 16, 1024));
-    const int64_t rec_limit = (int64_t)1 << kRecBits;
-    auto pair_cap_of = [&](int64_t c) {
-        if (world == 1) return 12 * c;
-        return std::min<int64_t>(12 * c, (int64_t)((double)(12 * c) / ((double)world * world) * 1.3) + 16384);
-    };
-    while (chunk > 1024 && ((int64_t)world * pair_cap_of(chunk) > rec_limit || 12 * chunk >= ((int64_t)1 << kCBits))) chunk /= 2;
+    chunk = std::min<int64_t>(chunk, ((int64_t)1 << 32) / 12 - 1);
     b->chunk_cap = chunk;
-    b->pair_cap = pair_cap_of(chunk);
-    if ((int64_t)world * b->pair_cap > rec_limit) return bail(ACS_ERR_UNSUPPORTED, "pbfs: exchange region too large");
+    // Record logs: every generated child that is not a self loop is appended to the (source ->
+    // owner) log and stays there (table slots point at log positions, so nothing is rewritten
+    // when a node is committed).  At most 12 records per expanded node; AC graphs produce ~2.2
+    // per visited node, the default budgets 3 (ACS_PBFS_LOG_FACTOR overrides) plus the last
+    // chunk's overshoot past the budget cut.
+    double factor = 3.0;
+    if (const char* f = std::getenv("ACS_PBFS_LOG_FACTOR")) factor = std::max(0.1, std::atof(f));
+    const double worst = 12.0 * (double)(max_nodes + 16 + chunk);
+    const double total = std::min(worst, factor * (double)max_nodes + 12.0 * (double)chunk + 1048576.0);
+    b->log_cap = world == 1 ? (int64_t)total + 64 : (int64_t)(total / ((double)world * world) * 1.15) + 65536;
+    if ((double)b->log_cap * world >= (double)(1ull << 40)) return bail(ACS_ERR_UNSUPPORTED, "pbfs: record log too large");
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) b->sms = prop.multiProcessorCount;
+    if (const char* g = std::getenv("ACS_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
 
     PbShard& S = b->S;
     S.W = b->W;
@@ -984,9 +1003,9 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     S.off_bitmap = off;
     off = align256(off + 2 * S.bitmap_words * 4);
     S.off_keys = off;
-    off = align256(off + 2 * (int64_t)world * b->pair_cap * 16 * b->W);
+    off = align256(off + (int64_t)world * b->log_cap * 16 * b->W);
     S.off_c = off;
-    off = align256(off + 2 * (int64_t)world * b->pair_cap * 4);
+    off = align256(off + (int64_t)world * b->log_cap * 4);
     b->arena_bytes = off;
 #define PB_ALLOC(ptr, bytes)                                                              \
     do {                                                                                  \
@@ -1002,12 +1021,12 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     PB_ALLOC(S.parent, (size_t)b->cap_local * 8);
     PB_ALLOC(S.gid, (size_t)b->cap_local * 8);
     PB_ALLOC(S.table, (size_t)b->tcap * 8);
-    PB_ALLOC(S.rec_slot, (size_t)world * b->pair_cap * 4);
     PB_ALLOC(S.bitmap_global, (size_t)S.bitmap_words * 4);
     PB_ALLOC(S.prefix_global, (size_t)(S.bitmap_words + 1) * 4);
     PB_ALLOC(S.prefix_local, (size_t)(S.bitmap_words + 1) * 4);
     PB_ALLOC(S.block_sums, (size_t)2 * S.nblk * 4);
     PB_ALLOC(S.cursors, kPbMaxWorld * 8);
+    PB_ALLOC(S.cstart, kPbMaxWorld * 8);
     PB_ALLOC(S.ctrl_local, kCtrlWords * 8);
     PB_ALLOC(b->d_path, (size_t)b->path_cap * 2 * sizeof(int32_t) + 16);
     PB_ALLOC(b->d_small, 8 * sizeof(long long));
@@ -1069,12 +1088,12 @@ void acs_pbfs_destroy(acs_pbfs* b) {
     cudaFree(S.parent);
     cudaFree(S.gid);
     cudaFree(S.table);
-    cudaFree(S.rec_slot);
     cudaFree(S.bitmap_global);
     cudaFree(S.prefix_global);
     cudaFree(S.prefix_local);
     cudaFree(S.block_sums);
     cudaFree(S.cursors);
+    cudaFree(S.cstart);
     cudaFree(S.ctrl_local);
     cudaFree(b->d_path);
     cudaFree(b->d_small);
@@ -1175,11 +1194,12 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         PB_CUDA(cudaSetDevice(b->device));
         cudaStream_t s = stream_of(b);
         PB_CUDA(cudaMemsetAsync(b->S.table, 0, b->tcap * sizeof(uint64_t), s));
+        PB_CUDA(cudaMemsetAsync(b->S.cursors, 0, kPbMaxWorld * 8, s));
         PbState st{};
         st.budget = b->budget;
         st.cap_local = b->cap_local;
         st.chunk_cap = b->chunk_cap;
-        st.pair_cap = b->pair_cap;
+        st.log_cap = b->log_cap;
         st.tmask = b->tcap - 1;
         st.mrl = b->mrl;
         st.cyclical = b->cyclical;
@@ -1197,12 +1217,20 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         b->h_ring[0] = st;  // pinned staging for the async upload
         PB_CUDA(cudaMemcpyAsync(b->S.st, &b->h_ring[0], sizeof(PbState), cudaMemcpyHostToDevice, s));
         if (b->rank == owner) {
-            const uint64_t slot_val = ((h >> 41) << 40) | 1ull;  // node index 0, stored +1
+            // the root is record 0 of the owner's own (owner -> owner) log, node 0 of its shard, and
+            // sits in the first slot of its 4-slot bucket (where the insert kernel's probe starts)
+            const uint64_t log_pos = (uint64_t)owner * (uint64_t)b->log_cap;
+            const uint64_t slot_val = ((h >> 41) << 40) | (log_pos + 1);
             const int64_t none = -1, zero = 0;
+            const unsigned long long one = 1;
+            const uint32_t c0 = 0;
+            char* arena = b->S.arena;
             PB_CUDA(cudaMemcpyAsync(b->S.keys, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+            PB_CUDA(cudaMemcpyAsync(arena + b->S.off_keys + log_pos * sizeof(root), &root, sizeof(root), cudaMemcpyHostToDevice, s));
+            PB_CUDA(cudaMemcpyAsync(arena + b->S.off_c + log_pos * 4, &c0, 4, cudaMemcpyHostToDevice, s));
+            PB_CUDA(cudaMemcpyAsync(b->S.cursors + owner, &one, 8, cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(b->S.parent, &none, 8, cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(b->S.gid, &zero, 8, cudaMemcpyHostToDevice, s));
-            // first slot of the key's 4-slot bucket: where the insert kernel's probe sequence starts
             PB_CUDA(cudaMemcpyAsync(b->S.table + ((h & (b->tcap - 1)) & ~3ull), &slot_val, 8, cudaMemcpyHostToDevice, s));
         }
         PB_CUDA(cudaStreamSynchronize(s));  // the staging copies above read host stack memory
@@ -1225,6 +1253,21 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
     };
     const int wide = b0->sms * 8;
     int rc = ACS_OK;
+    // ACS_PBFS_PROFILE=1: CUDA events after every phase of rank sh[0] -> per-phase totals on stderr
+    const bool profile = std::getenv("ACS_PBFS_PROFILE") != nullptr;
+    static const char* kPhaseNames[12] = {"prep", "expand", "signal0", "wait0", "insert", "signal1", "wait1",
+                                          "scan_sums", "scan_top", "scan_final", "decide", "commit"};
+    std::vector<cudaEvent_t> pev;
+    int phase_idx = 0;
+    auto mark = [&]() {
+        if (!profile) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, stream_of(b0));
+        pev.push_back(e);
+    };
+    (void)phase_idx;
+    mark();
     for (int64_t chunk = 0;; ++chunk) {
         if (chunk >= kLag) {
             PB_CUDA(cudaEventSynchronize(b0->ring_ev[(chunk - kLag) % kRing]));
@@ -1232,7 +1275,8 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         }
 #define PB_PHASE(expr)                                       \
     rc = each([&](acs_pbfs* b, cudaStream_t s) { expr; });   \
-    if (rc != ACS_OK) return rc;
+    if (rc != ACS_OK) return rc;                             \
+    mark();
         PB_PHASE((pb_prep_kernel<<<b->sms * 2, 256, 0, s>>>(b->S)));
         if (chunk == 0) {
             PB_PHASE((pb_expand_kernel<W, false><<<b->expand_blocks, 32 * b->expand_wpb, b->expand_smem, s>>>(b->S, b->expand_wpb)));
@@ -1240,11 +1284,14 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
             PB_PHASE((pb_expand_kernel<W, true><<<b->expand_blocks, 32 * b->expand_wpb, b->expand_smem, s>>>(b->S, b->expand_wpb)));
         }
         PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 0)));
-        if (world > 1) { PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 0, b->timeout_ns))); }
+        if (world > 1) { PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 0, b->timeout_ns))); } else mark();
         PB_PHASE((pb_insert_kernel<W><<<wide, 256, 0, s>>>(b->S)));
         if (world > 1) {
             PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 1)));
             PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 1, b->timeout_ns)));
+        } else {
+            mark();
+            mark();
         }
         PB_PHASE((pb_scan_sums_kernel<<<b->sms * 4, kScanT, 0, s>>>(b->S)));
         PB_PHASE((pb_scan_top_kernel<<<1, kScanT, 0, s>>>(b->S)));
@@ -1270,7 +1317,7 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
     const PbState& f = b0->h_final;
     if (ierr) {
         std::string m = "pbfs: internal error:";
-        if (ierr & IERR_PAIR_OVERFLOW) m += " exchange region overflow (skewed partition; pass a smaller chunk)";
+        if (ierr & IERR_LOG_FULL) m += " record log full (raise ACS_PBFS_LOG_FACTOR: this graph generates more than 3 children per visited state)";
         if (ierr & IERR_TABLE_FULL) m += " visited table full";
         if (ierr & IERR_SHARD_FULL) m += " shard capacity exceeded (skewed partition)";
         if (ierr & IERR_TIMEOUT) m += " timed out waiting for a peer rank";
@@ -1289,6 +1336,26 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
     float ms = 0.f;
     cudaEventElapsedTime(&ms, b0->ev0, b0->ev1);
     res->seconds_device = ms * 1e-3;
+    if (profile && pev.size() > 1) {
+        double tot[12] = {};
+        for (size_t k = 1; k < pev.size(); ++k) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, pev[k - 1], pev[k]);
+            tot[(k - 1) % 12] += t;
+        }
+        std::string line = "{\"pbfs_profile_ms\": {";
+        for (int k = 0; k < 12; ++k) {
+            char buf[64];
+            std::snprintf(buf, sizeof buf, "%s\"%s\": %.3f", k ? ", " : "", kPhaseNames[k], tot[k]);
+            line += buf;
+        }
+        char tail[160];
+        std::snprintf(tail, sizeof tail, "}, \"rank\": %d, \"world\": %d, \"chunks\": %lld, \"total_ms\": %.3f}\n", b0->rank, world,
+                      (long long)f.chunks, ms);
+        line += tail;
+        std::fputs(line.c_str(), stderr);
+        for (auto e : pev) cudaEventDestroy(e);
+    }
     if (f.solved && n_local == world && b0->d_shards && b0->n_group == world) {
         const int cap = std::min(path_cap, b0->path_cap);
         int32_t* d_len = b0->d_path + 2 * (size_t)b0->path_cap;
@@ -1354,7 +1421,7 @@ int acs_pbfs_visited(acs_pbfs* b, int64_t* h_gid, int8_t* h_rows, int64_t cap_ro
     return ACS_OK;
 }
 
-/* counters of the last run on this rank: {n_local, chunks, records sent, records received, chunk_cap, pair_cap,
+/* counters of the last run on this rank: {n_local, chunks, records sent, records received, chunk_cap, log_cap (records per source),
  * arena bytes, table slots} */
 int acs_pbfs_stats(acs_pbfs* b, int64_t* out8) {
     if (!b || !out8) return ACS_ERR_INVALID;
@@ -1363,7 +1430,7 @@ int acs_pbfs_stats(acs_pbfs* b, int64_t* out8) {
     out8[2] = (int64_t)b->h_final.records_sent;
     out8[3] = (int64_t)b->h_final.records_recv;
     out8[4] = b->chunk_cap;
-    out8[5] = b->pair_cap;
+    out8[5] = b->log_cap;
     out8[6] = b->arena_bytes;
     out8[7] = (int64_t)b->tcap;
     return ACS_OK;

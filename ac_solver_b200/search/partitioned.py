@@ -49,7 +49,7 @@ def _info(res, stats_list):
     st = stats_list[0]
     info.update(n_local=[int(s[0]) for s in stats_list], chunks=int(st[1]),
                 records_sent=[int(s[2]) for s in stats_list], records_recv=[int(s[3]) for s in stats_list],
-                chunk_cap=int(st[4]), pair_cap=int(st[5]), arena_bytes=int(st[6]), table_slots=int(st[7]))
+                chunk_cap=int(st[4]), log_cap=int(st[5]), arena_bytes=int(st[6]), table_slots=int(st[7]))
     return info
 
 

@@ -242,7 +242,7 @@ int acs_pbfs_run(acs_pbfs **shards, int n_local, const int8_t *h_presentation, i
 int acs_pbfs_lookup(acs_pbfs *b, int64_t gid, int64_t *out4);
 /* this rank's visited states and their global ids (= FIFO positions of the reference's tree_nodes) */
 int acs_pbfs_visited(acs_pbfs *b, int64_t *h_gid, int8_t *h_rows, int64_t cap_rows, int64_t *n_out);
-/* {n_local, chunks, records sent, records received, chunk_cap, pair_cap, arena bytes, table slots} */
+/* {n_local, chunks, records sent, records received, chunk_cap, record-log capacity per source, arena bytes, table slots} */
 int acs_pbfs_stats(acs_pbfs *b, int64_t *out8);
 int acs_pbfs_set_timeout(acs_pbfs *b, double seconds);
 void acs_pbfs_destroy(acs_pbfs *b);
