@@ -443,6 +443,17 @@ __device__ __forceinline__ bool is_tentative(const RegionMap* R, int world, int6
     return p - (uint64_t)s * (uint64_t)log_cap >= R->cstart[s];
 }
 
+// one 256-bit load of a 4-slot bucket (a 32-byte sector): ONE memory request.  Measured on B200
+// (scripts/microbench/random_access.cu): the chip sustains ~37 G random load requests/s whether
+// a request carries 8 or 32 bytes, and two 16-byte loads of one sector cost two requests.
+__device__ __forceinline__ void load_bucket(const uint64_t* p, uint64_t (&v)[4]) {
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+
+// The insert is bound by the number of divergent memory requests (see above), so it is written
+// for few of them: per record one bucket load, one log-key load per fingerprint match, one CAS
+// per claim; the winner-bitmap atomics of a warp fall into a few sectors (candidate ids of
+// consecutive log records are close), the record itself is read coalesced.
 template <int W>
 __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
     PbState* st = S.st;
@@ -451,6 +462,7 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
     load_regions(S, st, st->buf, &R);
     const unsigned long long total = R.vstart[S.world];
     const int64_t log_cap = st->log_cap;
+    const int world = S.world;
     const uint64_t* in_keys = sh_keys(S, S.arena);
     const uint32_t* in_c = sh_c(S, S.arena);
     uint32_t* bm = sh_bitmap(S, S.arena, st->buf);
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
     if (blockIdx.x == 0 && threadIdx.x == 0) st->records_recv += total;
     for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
          v += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t i = region_index(&R, S.world, log_cap, v);
+        const int64_t i = region_index(&R, world, log_cap, v);
         const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
         const uint32_t c = __ldcg(in_c + i);
         const uint64_t h = pb_hash<W>(key);
@@ -468,9 +480,8 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
         uint64_t probes = 0;
         bool finished = false;
         while (!finished) {
-            const ulonglong2 v01 = __ldcg(reinterpret_cast<const ulonglong2*>(S.table + s));
-            const ulonglong2 v23 = __ldcg(reinterpret_cast<const ulonglong2*>(S.table + s + 2));
-            const uint64_t vv[4] = {v01.x, v01.y, v23.x, v23.y};
+            uint64_t vv[4];
+            load_bucket(S.table + s, vv);
 #pragma unroll
             for (int jj = 0; jj < 4 && !finished; ++jj) {
                 uint64_t cur = vv[jj];
@@ -489,7 +500,7 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
                 if (!key_eq<W>(other, key)) continue;
                 // the same state: an older chunk's record (visited), or a record of this chunk --
                 // then the smaller candidate id keeps the slot (FIFO order of the reference)
-                if (is_tentative(&R, S.world, log_cap, p2)) {
+                if (is_tentative(&R, world, log_cap, p2)) {
                     for (;;) {
                         const uint32_t c2 = __ldcg(in_c + p2);
                         if (c2 < c) break;
@@ -927,7 +938,7 @@ struct acs_pbfs {
     PbState h_final{};
     uint64_t epoch = 0;
     int sms = 148;
-    int expand_wpb = 8, expand_blocks = 148;
+    int expand_wpb = 8, expand_blocks = 148, insert_blocks = 148, commit_blocks = 148;
     size_t expand_smem = 0;
     int32_t* d_path = nullptr;
     int path_cap = 1 << 16;
@@ -1061,6 +1072,17 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     if (b->W == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_expand_kernel<1, true>, 32 * wpb, b->expand_smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_expand_kernel<2, true>, 32 * wpb, b->expand_smem);
     b->expand_blocks = b->sms * std::max(per_sm, 1);
+    // persistent grid-stride kernels: exactly one wave of resident blocks
+    int ib = 1, cb = 1;
+    if (b->W == 1) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ib, pb_insert_kernel<1>, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cb, pb_commit_kernel<1>, 256, 0);
+    } else {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ib, pb_insert_kernel<2>, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cb, pb_commit_kernel<2>, 256, 0);
+    }
+    b->insert_blocks = b->sms * std::max(ib, 1);
+    b->commit_blocks = b->sms * std::max(cb, 1);
     for (int r = 0; r < kPbMaxWorld; ++r) S.peer[r] = nullptr;
     S.peer[rank] = S.arena;
     b->connected = world == 1;
@@ -1251,7 +1273,6 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         if (e != cudaSuccess) return pb_fail(ACS_ERR_CUDA, std::string("pbfs launch: ") + cudaGetErrorString(e));
         return ACS_OK;
     };
-    const int wide = b0->sms * 8;
     int rc = ACS_OK;
     // ACS_PBFS_PROFILE=1: CUDA events after every phase of rank sh[0] -> per-phase totals on stderr
     const bool profile = std::getenv("ACS_PBFS_PROFILE") != nullptr;
@@ -1285,7 +1306,7 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         }
         PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 0)));
         if (world > 1) { PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 0, b->timeout_ns))); } else mark();
-        PB_PHASE((pb_insert_kernel<W><<<wide, 256, 0, s>>>(b->S)));
+        PB_PHASE((pb_insert_kernel<W><<<b->insert_blocks, 256, 0, s>>>(b->S)));
         if (world > 1) {
             PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 1)));
             PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 1, b->timeout_ns)));
@@ -1297,7 +1318,7 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         PB_PHASE((pb_scan_top_kernel<<<1, kScanT, 0, s>>>(b->S)));
         PB_PHASE((pb_scan_final_kernel<<<b->sms * 4, kScanT, 0, s>>>(b->S)));
         PB_PHASE((pb_decide_kernel<<<1, kCtrlWords, 0, s>>>(b->S)));
-        PB_PHASE((pb_commit_kernel<W><<<wide, 256, 0, s>>>(b->S)));
+        PB_PHASE((pb_commit_kernel<W><<<b->commit_blocks, 256, 0, s>>>(b->S)));
 #undef PB_PHASE
         if (!same_device) PB_CUDA(cudaSetDevice(b0->device));
         PB_CUDA(cudaMemcpyAsync(&b0->h_ring[chunk % kRing], b0->S.st, sizeof(PbState), cudaMemcpyDeviceToHost, stream_of(b0)));
