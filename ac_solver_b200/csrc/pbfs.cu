@@ -92,28 +92,69 @@ struct PbState {
 // Pointers of one rank.  The "arena" part is visible to the peers (IPC or same process).
 struct PbShard {
     PbState* st;
-    uint64_t* keys;      // [cap][2W]
-    int64_t* parent;     // [cap]
-    int64_t* gid;        // [cap]
+    uint64_t* nodes;     // [cap][2W+2]  owned nodes in FIFO order: key words, parent link, global id
     uint64_t* table;     // [tmask+1]
-    uint32_t* bitmap_global;
-    uint32_t* prefix_global;  // [words+1]
-    uint32_t* prefix_local;   // [words+1]
-    uint32_t* block_sums;     // [2][nblk]
+    uint4* rt;           // [words+1] rank table: {global prefix, global bits, local prefix, local bits}
     unsigned long long* cursors;     // [world] append positions in the peers' record logs (persist over a run)
     unsigned long long* cstart;      // [world] their values at the start of the current chunk
     unsigned long long* ctrl_local;  // [kCtrlWords]
     // arena (same layout on every rank)
     char* arena;                     // own
     char* peer[kPbMaxWorld];         // peer arenas as seen from this process
-    int64_t off_flags;               // [2][world] u64
+    int64_t off_flags;               // [3 kinds][world] u64
     int64_t off_ctrl;                // [2 buf][world][kCtrlWords] u64
-    int64_t off_bitmap;              // [2 buf][bitmap_words] u32
+    int64_t off_bitmap;              // [2 buf][bitmap_words] u32   this rank's winner bits
+    int64_t off_bmg;                 // [bitmap_words] u32          all ranks' winner bits (filled slice-wise by the peers)
+    int64_t off_bsums;               // [2][nblk] u32               popcounts per scan block (global, local)
     int64_t off_keys;                // [world src][log_cap][2W] u64   record log: state keys ...
     int64_t off_c;                   // [world src][log_cap] u32        ... and candidate ids
     int64_t bitmap_words, nblk;
     int32_t W, world, rank, pad;
 };
+
+// node store: key words, then (parent global id << 4 | action) or -1, then the node's global id
+template <int W>
+__device__ __forceinline__ Key<W> node_key(const uint64_t* nodes, uint64_t idx) {
+    Key<W> q;
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nodes + idx * (2 * W + 2));
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const ulonglong2 v = p[i];
+        q.k[2 * i] = v.x;
+        q.k[2 * i + 1] = v.y;
+    }
+    return q;
+}
+template <int W>
+__device__ __forceinline__ void node_load(const uint64_t* nodes, uint64_t idx, Key<W>& q, int64_t& parent, int64_t& gid) {
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(nodes + idx * (2 * W + 2));
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const ulonglong2 v = p[i];
+        q.k[2 * i] = v.x;
+        q.k[2 * i + 1] = v.y;
+    }
+    const ulonglong2 t = p[W];
+    parent = (int64_t)t.x;
+    gid = (int64_t)t.y;
+}
+template <int W>
+__device__ __forceinline__ void node_store(uint64_t* nodes, uint64_t idx, const Key<W>& q, int64_t parent, int64_t gid) {
+    uint64_t* p = nodes + idx * (2 * W + 2);
+    if constexpr (W == 1) {  // one 256-bit store: one memory request per node
+        asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(q.k[0]), "l"(q.k[1]), "l"((uint64_t)parent),
+                     "l"((uint64_t)gid)
+                     : "memory");
+    } else {
+        ulonglong2* v = reinterpret_cast<ulonglong2*>(p);
+        v[0] = make_ulonglong2(q.k[0], q.k[1]);
+        v[1] = make_ulonglong2(q.k[2], q.k[3]);
+        v[2] = make_ulonglong2((uint64_t)parent, (uint64_t)gid);
+    }
+}
+__device__ __forceinline__ int64_t node_gid_rt(const uint64_t* nodes, int W, int64_t idx) {
+    return (int64_t)nodes[idx * (2 * W + 2) + 2 * W + 1];
+}
 
 __device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -170,6 +211,12 @@ __device__ __forceinline__ unsigned long long* sh_ctrl(const PbShard& S, char* b
 __device__ __forceinline__ uint32_t* sh_bitmap(const PbShard& S, char* base, int buf) {
     return reinterpret_cast<uint32_t*>(base + S.off_bitmap) + (int64_t)buf * S.bitmap_words;
 }
+__device__ __forceinline__ uint32_t* sh_bmg(const PbShard& S, char* base) {
+    return reinterpret_cast<uint32_t*>(base + S.off_bmg);
+}
+__device__ __forceinline__ uint32_t* sh_bsums(const PbShard& S, char* base) {
+    return reinterpret_cast<uint32_t*>(base + S.off_bsums);
+}
 __device__ __forceinline__ uint64_t* sh_keys(const PbShard& S, char* base) {
     return reinterpret_cast<uint64_t*>(base + S.off_keys);
 }
@@ -196,7 +243,7 @@ __global__ void __launch_bounds__(256) pb_prep_kernel(const PbShard S) {
         int64_t lo = l0, hi = st->n_local;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
-            if (S.gid[mid] < want) lo = mid + 1;
+            if (node_gid_rt(S.nodes, S.W, mid) < want) lo = mid + 1;
             else hi = mid;
         }
         st->l0 = l0;
@@ -219,7 +266,7 @@ __host__ __device__ constexpr size_t queue_bytes_per_warp(int world) {
 }
 
 template <int W>
-__device__ __forceinline__ void pb_flush(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int d, uint32_t n,
+__device__ __noinline__ void pb_flush(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int d, uint32_t n,
                                          int lane) {
     // n <= 32 records from the head of ring d go to rank d's inbox region (me -> d)
     unsigned long long pos = 0;
@@ -248,10 +295,27 @@ __device__ __forceinline__ void pb_flush(const PbShard& S, const PbState* st, Wa
 }
 
 template <int W>
-__device__ __noinline__ void pb_enqueue(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int dest,
-                                        const Key<W>& child, uint32_t c, int lane) {
+__device__ __forceinline__ void pb_enqueue(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int dest,
+                                           const Key<W>& child, uint32_t c, int lane) {
     const uint32_t act = __ballot_sync(0xFFFFFFFFu, dest >= 0);
     if (act == 0) return;
+    if (S.world == 1) {
+        // one destination: ring position from a ballot, no grouping needed
+        const uint32_t base = Q.cnt[0];
+        if (dest >= 0) {
+            const uint32_t q = (Q.head[0] + base + __popc(act & ((1u << lane) - 1u))) & (kQueue - 1);
+            uint64_t* sk = Q.keys + (size_t)q * 2 * W;
+#pragma unroll
+            for (int i = 0; i < 2 * W; ++i) sk[i] = child.k[i];
+            Q.c[q] = c;
+        }
+        __syncwarp();
+        const uint32_t total = base + __popc(act);
+        if (lane == 0) Q.cnt[0] = total;
+        __syncwarp();
+        if (total >= 32) pb_flush<W>(S, st, Q, 0, 32, lane);
+        return;
+    }
     bool lead_full = false;
     if (dest >= 0) {
         // lanes with the same destination reserve consecutive ring positions through their leader
@@ -318,10 +382,10 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
         uint64_t pg = 0;
         int back = -1;  // the move that undoes the one which created this node: its child is the node's own parent
         if (valid) {
-            pk = load_key<W>(S.keys, (uint64_t)j);
-            pg = (uint64_t)S.gid[j];
+            int64_t pl, gj;
+            node_load<W>(S.nodes, (uint64_t)j, pk, pl, gj);
+            pg = (uint64_t)gj;
             if (TRUSTED && !cyc) {
-                const int64_t pl = S.parent[j];
                 // inverse pairs: r1<-r1 r0 / r1<-r1 r0^-1 (0,2); r0<-r0 r1^-1 / r0<-r0 r1 (1,3); conjugation by g / g^-1
                 if (pl >= 0) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
             }
@@ -329,6 +393,7 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
         Rel<2 * W> p0, p1;
         split_key<W>(pk, p0, p1);
         const uint32_t cbase = (uint32_t)((pg - head) * 12);
+        const uint64_t gbase = pg * 12;
 #pragma unroll
         for (int a = 0; a < 12; ++a) {
             Rel<2 * W> r0 = p0, r1 = p1;
@@ -339,7 +404,7 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
             if (valid && a != back) {
                 bool co;
                 const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
-                const uint64_t gidc = pg * 12 + a;
+                const uint64_t gidc = gbase + a;
                 if (stt != ST_OK) {
                     atomicMin(&S.ctrl_local[kCtrlErr], (unsigned long long)((gidc << 2) | (unsigned)stt));
                 } else {
@@ -573,95 +638,108 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t& total)
     return before + x - v;
 }
 
-// OR of every rank's winner bitmap (peer loads) -> bitmap_global; popcount sums per scan block
+// Winner bits of all ranks, reduce-scatter / all-gather over peer memory: scan block b is combined
+// by rank b % world (OR of the G local bitmaps, peer loads) and the result stored into EVERY
+// rank's global bitmap together with its popcount, so a rank moves 2*(G-1)/G of a bitmap over
+// NVLink per chunk instead of reading G-1 whole bitmaps.  The local popcounts need no exchange.
 __global__ void __launch_bounds__(kScanT) pb_scan_sums_kernel(const PbShard S) {
     const PbState* st = S.st;
     if (st->done) return;
     const int64_t nwords = (12 * st->F + 31) / 32;
     const int64_t nblk = (nwords + kScanBlock - 1) / kScanBlock;
     const uint32_t* mine = sh_bitmap(S, S.arena, st->buf);
+    uint32_t* my_sums = sh_bsums(S, S.arena);
     for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
+        const bool combine = (int)(b % S.world) == S.rank;
         uint32_t sg = 0, sl = 0;
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
             const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
             if (i < nwords) {
                 const uint32_t loc = __ldcg(mine + i);
-                uint32_t g = loc;
-                for (int r = 0; r < S.world; ++r)
-                    if (r != S.rank) g |= __ldcv(sh_bitmap(S, S.peer[r], st->buf) + i);
-                S.bitmap_global[i] = g;
-                sg += __popc(g);
                 sl += __popc(loc);
+                if (combine) {
+                    uint32_t g = loc;
+                    for (int r = 0; r < S.world; ++r)
+                        if (r != S.rank) g |= __ldcv(sh_bitmap(S, S.peer[r], st->buf) + i);
+                    for (int r = 0; r < S.world; ++r) sh_bmg(S, S.peer[r])[i] = g;
+                    sg += __popc(g);
+                }
             }
         }
         block_sum2(sg, sl);
         if (threadIdx.x == 0) {
-            S.block_sums[b] = sg;
-            S.block_sums[S.nblk + b] = sl;
+            my_sums[S.nblk + b] = sl;
+            if (combine)
+                for (int r = 0; r < S.world; ++r) sh_bsums(S, S.peer[r])[b] = sg;
         }
         __syncthreads();
     }
+    __threadfence_system();
 }
-// single block: exclusive scans of both block-sum arrays in place; totals to prefix[nwords]
+// single block: exclusive scans of both block-sum arrays in place; totals to the last rank-table entry
 __global__ void __launch_bounds__(kScanT) pb_scan_top_kernel(const PbShard S) {
     const PbState* st = S.st;
     if (st->done) return;
     const int64_t nwords = (12 * st->F + 31) / 32;
     const int64_t nblk = (nwords + kScanBlock - 1) / kScanBlock;
+    uint32_t tot[2] = {0, 0};
     for (int which = 0; which < 2; ++which) {
-        uint32_t* sums = S.block_sums + which * S.nblk;
+        uint32_t* sums = sh_bsums(S, S.arena) + which * S.nblk;
         uint32_t carry = 0;
         for (int64_t base = 0; base < nblk; base += kScanT) {
             const int64_t i = base + threadIdx.x;
-            const uint32_t v = i < nblk ? sums[i] : 0u;
+            const uint32_t v = i < nblk ? __ldcg(sums + i) : 0u;
             uint32_t total;
             const uint32_t ex = block_excl_scan(v, total);
             if (i < nblk) sums[i] = carry + ex;
             carry += total;
             __syncthreads();
         }
-        if (threadIdx.x == 0) (which == 0 ? S.prefix_global : S.prefix_local)[nwords] = carry;
+        tot[which] = carry;
     }
+    if (threadIdx.x == 0) S.rt[nwords] = make_uint4(tot[0], 0u, tot[1], 0u);
 }
+// rank table: per bitmap word {winners before it (all ranks), its bits (all ranks), same for this rank}
 __global__ void __launch_bounds__(kScanT) pb_scan_final_kernel(const PbShard S) {
     const PbState* st = S.st;
     if (st->done) return;
     const int64_t nwords = (12 * st->F + 31) / 32;
     const int64_t nblk = (nwords + kScanBlock - 1) / kScanBlock;
     const uint32_t* loc = sh_bitmap(S, S.arena, st->buf);
+    const uint32_t* glob = sh_bmg(S, S.arena);
+    const uint32_t* sums = sh_bsums(S, S.arena);
     for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
         const int64_t first = b * kScanBlock + (int64_t)threadIdx.x * kScanPer;
-        uint32_t cg[kScanPer], cl[kScanPer];
+        uint32_t wg[kScanPer], wl[kScanPer];
         uint32_t sg = 0, sl = 0;
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
             const bool in = first + k < nwords;
-            cg[k] = in ? __popc(S.bitmap_global[first + k]) : 0u;
-            cl[k] = in ? __popc(__ldcg(loc + first + k)) : 0u;
-            sg += cg[k];
-            sl += cl[k];
+            wg[k] = in ? __ldcg(glob + first + k) : 0u;
+            wl[k] = in ? __ldcg(loc + first + k) : 0u;
+            sg += __popc(wg[k]);
+            sl += __popc(wl[k]);
         }
         uint32_t tg, tl;
-        uint32_t rg = S.block_sums[b] + block_excl_scan(sg, tg);
+        uint32_t rg = sums[b] + block_excl_scan(sg, tg);
         __syncthreads();
-        uint32_t rl = S.block_sums[S.nblk + b] + block_excl_scan(sl, tl);
+        uint32_t rl = sums[S.nblk + b] + block_excl_scan(sl, tl);
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
-            if (first + k < nwords) {
-                S.prefix_global[first + k] = rg;
-                S.prefix_local[first + k] = rl;
-            }
-            rg += cg[k];
-            rl += cl[k];
+            if (first + k < nwords) S.rt[first + k] = make_uint4(rg, wg[k], rl, wl[k]);
+            rg += __popc(wg[k]);
+            rl += __popc(wl[k]);
         }
         __syncthreads();
     }
 }
 
-__device__ __forceinline__ uint32_t bm_rank(const uint32_t* bitmap, const uint32_t* prefix, uint64_t c) {
-    const uint32_t r = (uint32_t)(c & 31);
-    return prefix[c >> 5] + (r ? __popc(bitmap[c >> 5] & ((1u << r) - 1u)) : 0u);
+// winners with candidate id < c: .x over all ranks, .y on this rank (one 16-byte load)
+__device__ __forceinline__ uint2 rt_rank(const uint4* rt, uint64_t c) {
+    const uint4 e = rt[c >> 5];
+    const uint32_t m = (1u << (c & 31)) - 1u;
+    return make_uint2(e.x + __popc(e.y & m), e.z + __popc(e.w & m));
 }
 
 // ---- decide ----------------------------------------------------------------------------------
@@ -684,11 +762,10 @@ __global__ void __launch_bounds__(kCtrlWords) pb_decide_kernel(const PbShard S) 
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
-    const uint32_t* bl = sh_bitmap(S, S.arena, st->buf);
     const uint64_t F = (uint64_t)st->F, head = (uint64_t)st->head, n_nodes = (uint64_t)st->n_nodes;
     const uint64_t budget = (uint64_t)st->budget;
     const int64_t nwords = (12 * (int64_t)F + 31) / 32;
-    const uint64_t total = S.prefix_global[nwords];
+    const uint64_t total = S.rt[nwords].x;
     uint64_t limit = 12 * F;
     bool cut = false;
     uint64_t cut_p = 0;
@@ -697,7 +774,7 @@ __global__ void __launch_bounds__(kCtrlWords) pb_decide_kernel(const PbShard S) 
         uint64_t lo = 0, hi = F - 1;
         while (lo < hi) {
             const uint64_t mid = (lo + hi) >> 1;
-            if (n_nodes + bm_rank(S.bitmap_global, S.prefix_global, (mid + 1) * 12) >= budget) hi = mid;
+            if (n_nodes + rt_rank(S.rt, (mid + 1) * 12).x >= budget) hi = mid;
             else lo = mid + 1;
         }
         cut = true;
@@ -737,8 +814,8 @@ __global__ void __launch_bounds__(kCtrlWords) pb_decide_kernel(const PbShard S) 
         if (st->n_minlen < 128) st->minlen_log[st->n_minlen++] = bestL;
     }
     st->min_len = min_len;
-    const uint64_t cg = bm_rank(S.bitmap_global, S.prefix_global, limit);
-    const uint64_t cl = bm_rank(bl, S.prefix_local, limit);
+    const uint2 at_limit = rt_rank(S.rt, limit);
+    const uint64_t cg = at_limit.x, cl = at_limit.y;
     st->limit = (int64_t)limit;
     st->head0 = st->head;
     st->commit_pending = 1;
@@ -809,7 +886,6 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
     const int64_t log_cap = st->log_cap;
     const uint64_t* in_keys = sh_keys(S, S.arena);
     const uint32_t* in_c = sh_c(S, S.arena);
-    const uint32_t* bl = sh_bitmap(S, S.arena, buf);
     const uint64_t limit = (uint64_t)st->limit;
     const uint64_t n_nodes0 = (uint64_t)st->n_nodes0, n_local0 = (uint64_t)st->n_local0;
     const uint64_t head0 = (uint64_t)st->head0;
@@ -818,13 +894,14 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
         const int64_t i = region_index(&R, S.world, log_cap, v);
         const uint64_t c = __ldcg(in_c + i);
         if (c >= limit) continue;
-        if (!((__ldcg(bl + (c >> 5)) >> (c & 31)) & 1u)) continue;  // an already visited state, or lost to an earlier candidate
-        const uint64_t g = n_nodes0 + bm_rank(S.bitmap_global, S.prefix_global, c);
-        const uint64_t idx = n_local0 + bm_rank(bl, S.prefix_local, c);
+        const uint4 e = S.rt[c >> 5];
+        if (!((e.w >> (c & 31)) & 1u)) continue;  // an already visited state, or lost to an earlier candidate
+        const uint32_t m = (1u << (c & 31)) - 1u;
+        const uint64_t g = n_nodes0 + e.x + __popc(e.y & m);
+        const uint64_t idx = n_local0 + e.z + __popc(e.w & m);
         if (idx >= (uint64_t)st->cap_local) continue;  // IERR_SHARD_FULL was raised by decide
-        store_key<W>(S.keys, idx, load_key_cg<W>(in_keys, (uint64_t)i));
-        S.parent[idx] = (int64_t)(((head0 + c / 12) << 4) | (c % 12));
-        S.gid[idx] = (int64_t)g;
+        node_store<W>(S.nodes, idx, load_key_cg<W>(in_keys, (uint64_t)i), (int64_t)(((head0 + c / 12) << 4) | (c % 12)),
+                      (int64_t)g);
     }
 }
 
@@ -833,11 +910,11 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
 namespace acs {
 
 // one thread: smallest local index with gid >= value
-__device__ __forceinline__ int64_t pb_lower_bound(const int64_t* gid, int64_t n, int64_t value) {
+__device__ __forceinline__ int64_t pb_lower_bound(const uint64_t* nodes, int W, int64_t n, int64_t value) {
     int64_t lo = 0, hi = n;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (gid[mid] < value) lo = mid + 1;
+        if (node_gid_rt(nodes, W, mid) < value) lo = mid + 1;
         else hi = mid;
     }
     return lo;
@@ -847,15 +924,32 @@ __device__ __forceinline__ int64_t pb_lower_bound(const int64_t* gid, int64_t n,
 template <int W>
 __global__ void pb_lookup_kernel(const PbShard S, int64_t value, long long* out) {
     const int64_t n = S.st->n_local;
-    const int64_t lo = pb_lower_bound(S.gid, n, value);
+    const int64_t lo = pb_lower_bound(S.nodes, W, n, value);
     out[0] = out[1] = out[2] = out[3] = 0;
-    if (lo < n && S.gid[lo] == value) {
-        const Key<W> k = load_key<W>(S.keys, (uint64_t)lo);
+    Key<W> k;
+    int64_t par = 0, g = -1;
+    if (lo < n) node_load<W>(S.nodes, (uint64_t)lo, k, par, g);
+    if (lo < n && g == value) {
         out[0] = 1;
-        out[1] = S.parent[lo] < 0 ? -1 : (S.parent[lo] >> 4);
-        out[2] = S.parent[lo] < 0 ? -1 : (S.parent[lo] & 15);
+        out[1] = par < 0 ? -1 : (par >> 4);
+        out[2] = par < 0 ? -1 : (par & 15);
         out[3] = (long long)(k.k[W - 1] >> 58) + (long long)(k.k[2 * W - 1] >> 58);
     }
+}
+
+// visited nodes -> int8 rows and global ids (local order)
+template <int W>
+__global__ void pb_unpack_kernel(const uint64_t* nodes, int8_t* out, int64_t* gid_out, uint64_t n, int mrl) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Key<W> k;
+    int64_t par, g;
+    node_load<W>(nodes, i, k, par, g);
+    Rel<2 * W> r0, r1;
+    split_key<W>(k, r0, r1);
+    unpack_bytes<2 * W>(out + i * 2 * mrl, r0, mrl);
+    unpack_bytes<2 * W>(out + i * 2 * mrl + mrl, r1, mrl);
+    gid_out[i] = g;
 }
 
 // all shards in this process: path of node `node` from the root, then (extra_action, extra_len)
@@ -871,12 +965,14 @@ __global__ void pb_path_kernel(const PbShard* shards, int n_shards, int64_t node
             for (int s = 0; s < n_shards; ++s) {
                 const PbShard& S = shards[s];
                 const int64_t n = S.st->n_local;
-                const int64_t lo = pb_lower_bound(S.gid, n, g);
-                if (lo < n && S.gid[lo] == g) {
-                    const Key<W> k = load_key<W>(S.keys, (uint64_t)lo);
+                const int64_t lo = pb_lower_bound(S.nodes, W, n, g);
+                Key<W> k;
+                int64_t pl = 0, gg = -1;
+                if (lo < n) node_load<W>(S.nodes, (uint64_t)lo, k, pl, gg);
+                if (lo < n && gg == g) {
                     L = (int)(k.k[W - 1] >> 58) + (int)(k.k[2 * W - 1] >> 58);
-                    par = S.parent[lo] < 0 ? -1 : (S.parent[lo] >> 4);
-                    act = S.parent[lo] < 0 ? -1 : (int)(S.parent[lo] & 15);
+                    par = pl < 0 ? -1 : (pl >> 4);
+                    act = pl < 0 ? -1 : (int)(pl & 15);
                     break;
                 }
             }
@@ -1008,11 +1104,16 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     S.nblk = (S.bitmap_words + kScanBlock - 1) / kScanBlock + 1;
     int64_t off = 0;
     S.off_flags = off;
-    off = align256(off + 2 * (int64_t)world * 8);
+    off = align256(off + 3 * (int64_t)world * 8);
     S.off_ctrl = off;
     off = align256(off + 2 * (int64_t)world * kCtrlWords * 8);
+    const int64_t zero_bytes = off;  // flags / control inboxes start at zero (epochs start at 1)
     S.off_bitmap = off;
     off = align256(off + 2 * S.bitmap_words * 4);
+    S.off_bmg = off;
+    off = align256(off + S.bitmap_words * 4);
+    S.off_bsums = off;
+    off = align256(off + 2 * S.nblk * 4);
     S.off_keys = off;
     off = align256(off + (int64_t)world * b->log_cap * 16 * b->W);
     S.off_c = off;
@@ -1028,14 +1129,9 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     } while (0)
     PB_ALLOC(S.arena, b->arena_bytes);
     PB_ALLOC(S.st, sizeof(PbState));
-    PB_ALLOC(S.keys, (size_t)b->cap_local * 16 * b->W);
-    PB_ALLOC(S.parent, (size_t)b->cap_local * 8);
-    PB_ALLOC(S.gid, (size_t)b->cap_local * 8);
+    PB_ALLOC(S.nodes, (size_t)b->cap_local * 8 * (2 * b->W + 2));
     PB_ALLOC(S.table, (size_t)b->tcap * 8);
-    PB_ALLOC(S.bitmap_global, (size_t)S.bitmap_words * 4);
-    PB_ALLOC(S.prefix_global, (size_t)(S.bitmap_words + 1) * 4);
-    PB_ALLOC(S.prefix_local, (size_t)(S.bitmap_words + 1) * 4);
-    PB_ALLOC(S.block_sums, (size_t)2 * S.nblk * 4);
+    PB_ALLOC(S.rt, (size_t)(S.bitmap_words + 1) * sizeof(uint4));
     PB_ALLOC(S.cursors, kPbMaxWorld * 8);
     PB_ALLOC(S.cstart, kPbMaxWorld * 8);
     PB_ALLOC(S.ctrl_local, kCtrlWords * 8);
@@ -1043,7 +1139,7 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     PB_ALLOC(b->d_small, 8 * sizeof(long long));
 #undef PB_ALLOC
     // flags / control inboxes start at zero (epochs start at 1)
-    if (cudaMemset(S.arena, 0, (size_t)S.off_bitmap) != cudaSuccess) return bail(ACS_ERR_CUDA, "pbfs: memset(arena)");
+    if (cudaMemset(S.arena, 0, (size_t)zero_bytes) != cudaSuccess) return bail(ACS_ERR_CUDA, "pbfs: memset(arena)");
     if (cudaMallocHost((void**)&b->h_ring, kRing * sizeof(PbState)) != cudaSuccess)
         return bail(ACS_ERR_NOMEM, "pbfs: cudaMallocHost");
     if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -1106,14 +1202,9 @@ void acs_pbfs_destroy(acs_pbfs* b) {
     PbShard& S = b->S;
     cudaFree(S.arena);
     cudaFree(S.st);
-    cudaFree(S.keys);
-    cudaFree(S.parent);
-    cudaFree(S.gid);
+    cudaFree(S.nodes);
     cudaFree(S.table);
-    cudaFree(S.bitmap_global);
-    cudaFree(S.prefix_global);
-    cudaFree(S.prefix_local);
-    cudaFree(S.block_sums);
+    cudaFree(S.rt);
     cudaFree(S.cursors);
     cudaFree(S.cstart);
     cudaFree(S.ctrl_local);
@@ -1247,12 +1338,14 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
             const unsigned long long one = 1;
             const uint32_t c0 = 0;
             char* arena = b->S.arena;
-            PB_CUDA(cudaMemcpyAsync(b->S.keys, &root, sizeof(root), cudaMemcpyHostToDevice, s));
+            uint64_t node0[2 * W + 2];
+            for (int k = 0; k < 2 * W; ++k) node0[k] = root.k[k];
+            node0[2 * W] = (uint64_t)none;
+            node0[2 * W + 1] = (uint64_t)zero;
+            PB_CUDA(cudaMemcpyAsync(b->S.nodes, node0, sizeof(node0), cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(arena + b->S.off_keys + log_pos * sizeof(root), &root, sizeof(root), cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(arena + b->S.off_c + log_pos * 4, &c0, 4, cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(b->S.cursors + owner, &one, 8, cudaMemcpyHostToDevice, s));
-            PB_CUDA(cudaMemcpyAsync(b->S.parent, &none, 8, cudaMemcpyHostToDevice, s));
-            PB_CUDA(cudaMemcpyAsync(b->S.gid, &zero, 8, cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(b->S.table + ((h & (b->tcap - 1)) & ~3ull), &slot_val, 8, cudaMemcpyHostToDevice, s));
         }
         PB_CUDA(cudaStreamSynchronize(s));  // the staging copies above read host stack memory
@@ -1276,8 +1369,8 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
     int rc = ACS_OK;
     // ACS_PBFS_PROFILE=1: CUDA events after every phase of rank sh[0] -> per-phase totals on stderr
     const bool profile = std::getenv("ACS_PBFS_PROFILE") != nullptr;
-    static const char* kPhaseNames[12] = {"prep", "expand", "signal0", "wait0", "insert", "signal1", "wait1",
-                                          "scan_sums", "scan_top", "scan_final", "decide", "commit"};
+    static const char* kPhaseNames[14] = {"prep", "expand", "signal0", "wait0", "insert", "signal1", "wait1",
+                                          "scan_sums", "signal2", "wait2", "scan_top", "scan_final", "decide", "commit"};
     std::vector<cudaEvent_t> pev;
     int phase_idx = 0;
     auto mark = [&]() {
@@ -1315,6 +1408,13 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
             mark();
         }
         PB_PHASE((pb_scan_sums_kernel<<<b->sms * 4, kScanT, 0, s>>>(b->S)));
+        if (world > 1) {
+            PB_PHASE((pb_signal_kernel<<<1, 256, 0, s>>>(b->S, 2)));
+            PB_PHASE((pb_wait_kernel<<<1, 32, 0, s>>>(b->S, 2, b->timeout_ns)));
+        } else {
+            mark();
+            mark();
+        }
         PB_PHASE((pb_scan_top_kernel<<<1, kScanT, 0, s>>>(b->S)));
         PB_PHASE((pb_scan_final_kernel<<<b->sms * 4, kScanT, 0, s>>>(b->S)));
         PB_PHASE((pb_decide_kernel<<<1, kCtrlWords, 0, s>>>(b->S)));
@@ -1358,14 +1458,14 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
     cudaEventElapsedTime(&ms, b0->ev0, b0->ev1);
     res->seconds_device = ms * 1e-3;
     if (profile && pev.size() > 1) {
-        double tot[12] = {};
+        double tot[14] = {};
         for (size_t k = 1; k < pev.size(); ++k) {
             float t = 0.f;
             cudaEventElapsedTime(&t, pev[k - 1], pev[k]);
-            tot[(k - 1) % 12] += t;
+            tot[(k - 1) % 14] += t;
         }
         std::string line = "{\"pbfs_profile_ms\": {";
-        for (int k = 0; k < 12; ++k) {
+        for (int k = 0; k < 14; ++k) {
             char buf[64];
             std::snprintf(buf, sizeof buf, "%s\"%s\": %.3f", k ? ", " : "", kPhaseNames[k], tot[k]);
             line += buf;
@@ -1431,12 +1531,19 @@ int acs_pbfs_visited(acs_pbfs* b, int64_t* h_gid, int8_t* h_rows, int64_t cap_ro
     if (n_out) *n_out = n;
     if (n == 0) return ACS_OK;
     int8_t* d = nullptr;
+    int64_t* dg = nullptr;
     PB_CUDA(cudaMalloc((void**)&d, (size_t)n * 2 * b->mrl));
-    if (b->W == 1) keys_unpack_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->S.keys, d, (uint64_t)n, b->mrl);
-    else keys_unpack_kernel<2><<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->S.keys, d, (uint64_t)n, b->mrl);
+    if (cudaMalloc((void**)&dg, (size_t)n * 8) != cudaSuccess) {
+        cudaFree(d);
+        cudaGetLastError();
+        return pb_fail(ACS_ERR_NOMEM, "pbfs: cudaMalloc(visited ids)");
+    }
+    if (b->W == 1) pb_unpack_kernel<1><<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->S.nodes, d, dg, (uint64_t)n, b->mrl);
+    else pb_unpack_kernel<2><<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(b->S.nodes, d, dg, (uint64_t)n, b->mrl);
     cudaError_t e = cudaMemcpyAsync(h_rows, d, (size_t)n * 2 * b->mrl, cudaMemcpyDeviceToHost, b->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(h_gid, b->S.gid, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_gid, dg, (size_t)n * 8, cudaMemcpyDeviceToHost, b->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    cudaFree(dg);
     cudaFree(d);
     PB_CUDA(e);
     return ACS_OK;
