@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, *srcs]
+    extra = os.environ.get("ACS_NVCC_EXTRA", "").split()  # e.g. -DPB_UNROLL=1 for kernel experiments
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, *srcs]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -64,7 +64,6 @@ constexpr int kCtrlWords = 136;        // sol, err, first_len[128], log end, ier
 constexpr int kCtrlSol = 0, kCtrlErr = 1, kCtrlLen0 = 2, kCtrlCount = 130, kCtrlIerr = 131, kCtrlStart = 132;
 // table slot: 23-bit fingerprint << 40 | (record-log position + 1); 0 = empty
 constexpr uint64_t kPosMask = (1ull << 40) - 1;
-constexpr int kQueue = 64;              // per-warp, per-destination staging ring (records)
 constexpr int kScanT = 256, kScanPer = 8, kScanBlock = kScanT * kScanPer;  // words per scan block
 
 enum : int { IERR_LOG_FULL = 1, IERR_TABLE_FULL = 2, IERR_SHARD_FULL = 4, IERR_TIMEOUT = 8 };
@@ -185,9 +184,20 @@ __host__ __device__ __forceinline__ uint64_t pb_hash(const Key<W>& q) {
     h ^= h >> 32;
     return h;
 }
-__host__ __device__ __forceinline__ int pb_owner(uint64_t h, int world) {
-    const uint32_t m = (uint32_t)((h * 0xFF51AFD7ED558CCDull) >> 32);
-    return (int)(((uint64_t)m * (uint32_t)world) >> 32);
+// Owner rank of a state: a cheap 32-bit multiply-xor hash of the key words, a different function
+// from pb_hash so that the owner is independent of the table slot and fingerprint bits.
+template <int W>
+__host__ __device__ __forceinline__ int pb_owner(const Key<W>& q, int world) {
+    uint32_t x = 0x9E3779B9u;
+#pragma unroll
+    for (int i = 0; i < 2 * W; ++i) {
+        x = (x ^ (uint32_t)q.k[i]) * 0x85EBCA6Bu;
+        x = (x ^ (x >> 15) ^ (uint32_t)(q.k[i] >> 32)) * 0xC2B2AE35u;
+    }
+    x ^= x >> 16;
+    x *= 0x7FEB352Du;
+    x ^= x >> 15;
+    return (int)(((uint64_t)x * (uint32_t)world) >> 32);
 }
 
 template <int W>
@@ -252,126 +262,173 @@ __global__ void __launch_bounds__(256) pb_prep_kernel(const PbShard S) {
 }
 
 // ---- expand ----------------------------------------------------------------------------------
-// Per-warp staging: for every destination a ring of kQueue records (key + candidate id).
+// Per-warp staging in shared memory: kStage records (key, candidate id, destination rank) in
+// generation order, a second buffer of the same size for the destination-sorted copy, and the
+// per-destination counters of the flush.  The size does not depend on the world size.
+constexpr int kStage = 128;
+#ifndef PB_UNROLL
+#define PB_UNROLL 4
+#endif
+constexpr int kPbUnroll = PB_UNROLL;  // of the 12-move loop in the expansion kernel
 template <int W>
-struct WarpQueues {
-    uint64_t* keys;  // [world][kQueue][2W]
-    uint32_t* c;     // [world][kQueue]
-    uint32_t* cnt;   // [world]
-    uint32_t* head;  // [world] 0 or 32
+__host__ __device__ constexpr int stage_bytes_per_warp() {
+    return 2 * kStage * (16 * W + 4 + 4) + kPbMaxWorld * (4 + 4 + 8);
+}
+extern __shared__ __align__(16) unsigned char pb_smem[];
+template <int W>
+struct Stage {
+    ulonglong2* keys;  // [kStage][W]
+    uint32_t* c;       // [kStage]
+    uint32_t* dest;    // [kStage]
+    ulonglong2* keys2;
+    uint32_t* c2;
+    uint32_t* dest2;
+    uint32_t* cnt;     // [kPbMaxWorld]
+    uint32_t* off;     // [kPbMaxWorld]
+    unsigned long long* gpos;  // [kPbMaxWorld]
+    __device__ __forceinline__ explicit Stage(int wib) {
+        unsigned char* p = pb_smem + wib * stage_bytes_per_warp<W>();
+        keys = reinterpret_cast<ulonglong2*>(p);
+        keys2 = reinterpret_cast<ulonglong2*>(p + kStage * 16 * W);
+        gpos = reinterpret_cast<unsigned long long*>(p + 2 * kStage * 16 * W);
+        uint32_t* q = reinterpret_cast<uint32_t*>(p + 2 * kStage * 16 * W + kPbMaxWorld * 8);
+        c = q;
+        dest = q + kStage;
+        c2 = q + 2 * kStage;
+        dest2 = q + 3 * kStage;
+        cnt = q + 4 * kStage;
+        off = cnt + kPbMaxWorld;
+    }
 };
-template <int W>
-__host__ __device__ constexpr size_t queue_bytes_per_warp(int world) {
-    return (size_t)world * (kQueue * (16 * W + 4) + 8);
-}
+// block-wide: where this rank's records go in every destination's log
+struct DestBase {
+    ulonglong2* keys[kPbMaxWorld];
+    uint32_t* c[kPbMaxWorld];
+};
 
+// Flush the n staged records of this warp: a counting sort by destination rank in shared memory,
+// ONE atomic instruction reserving space in all destination logs (local atomics: every (source,
+// destination) pair has its own log), then runs of coalesced stores straight into the
+// destinations' memory -- peer stores over NVLink when the destination is another GPU.  This is
+// the all-to-all of the search, fused into the expansion kernel.
 template <int W>
-__device__ __noinline__ void pb_flush(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int d, uint32_t n,
-                                         int lane) {
-    // n <= 32 records from the head of ring d go to rank d's inbox region (me -> d)
-    unsigned long long pos = 0;
-    if (lane == 0) pos = atomicAdd(&S.cursors[d], (unsigned long long)n);
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    const uint32_t hd = Q.head[d];
-    if (pos + n > (unsigned long long)st->log_cap) {
-        if (lane == 0) atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_LOG_FULL);
-    } else if ((uint32_t)lane < n) {
-        const uint32_t q = (hd + lane) & (kQueue - 1);
-        char* base = S.peer[d];
-        const int64_t r = (int64_t)S.rank * st->log_cap + (int64_t)pos + lane;
-        uint64_t* dk = sh_keys(S, base) + r * 2 * W;
-        const uint64_t* sk = Q.keys + ((size_t)d * kQueue + q) * 2 * W;
+__device__ __noinline__ void pb_flush(const PbShard& S, const DestBase* DB, int wib, uint32_t n, int lane,
+                                      int64_t log_cap, int world) {
+    Stage<W> Q(wib);
+    if (world == 1) {
+        unsigned long long pos = 0;
+        if (lane == 0) pos = atomicAdd(&S.cursors[0], (unsigned long long)n);
+        pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+        if (pos + n > (unsigned long long)log_cap) {
+            if (lane == 0) atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_LOG_FULL);
+        } else {
+            ulonglong2* dk = DB->keys[0] + pos * W;
+            uint32_t* dc = DB->c[0] + pos;
 #pragma unroll
-        for (int i = 0; i < W; ++i)
-            reinterpret_cast<ulonglong2*>(dk)[i] = make_ulonglong2(sk[2 * i], sk[2 * i + 1]);
-        sh_c(S, base)[r] = Q.c[d * kQueue + q];
-    }
-    __syncwarp();
-    if (lane == 0) {
-        Q.head[d] = (hd + n) & (kQueue - 1);
-        Q.cnt[d] -= n;
-    }
-    __syncwarp();
-}
-
-template <int W>
-__device__ __forceinline__ void pb_enqueue(const PbShard& S, const PbState* st, WarpQueues<W>& Q, int dest,
-                                           const Key<W>& child, uint32_t c, int lane) {
-    const uint32_t act = __ballot_sync(0xFFFFFFFFu, dest >= 0);
-    if (act == 0) return;
-    if (S.world == 1) {
-        // one destination: ring position from a ballot, no grouping needed
-        const uint32_t base = Q.cnt[0];
-        if (dest >= 0) {
-            const uint32_t q = (Q.head[0] + base + __popc(act & ((1u << lane) - 1u))) & (kQueue - 1);
-            uint64_t* sk = Q.keys + (size_t)q * 2 * W;
+            for (int r = 0; r < kStage / 32; ++r) {
+                const uint32_t idx = r * 32 + lane;
+                if (idx < n) {
 #pragma unroll
-            for (int i = 0; i < 2 * W; ++i) sk[i] = child.k[i];
-            Q.c[q] = c;
+                    for (int i = 0; i < W; ++i) dk[(size_t)idx * W + i] = Q.keys[idx * W + i];
+                    dc[idx] = Q.c[idx];
+                }
+            }
         }
         __syncwarp();
-        const uint32_t total = base + __popc(act);
-        if (lane == 0) Q.cnt[0] = total;
-        __syncwarp();
-        if (total >= 32) pb_flush<W>(S, st, Q, 0, 32, lane);
         return;
     }
-    bool lead_full = false;
-    if (dest >= 0) {
-        // lanes with the same destination reserve consecutive ring positions through their leader
-        const uint32_t grp = __match_any_sync(act, dest);
-        const int leader = __ffs(grp) - 1;
-        uint32_t base = 0;
-        if (lane == leader) {
-            base = Q.cnt[dest];
-            Q.cnt[dest] = base + __popc(grp);
-        }
-        base = __shfl_sync(grp, base, leader);
-        const uint32_t q = (Q.head[dest] + base + __popc(grp & ((1u << lane) - 1u))) & (kQueue - 1);
-        uint64_t* sk = Q.keys + ((size_t)dest * kQueue + q) * 2 * W;
+    if (lane < kPbMaxWorld) Q.cnt[lane] = 0;
+    __syncwarp();
+    uint32_t d[kStage / 32], rk[kStage / 32];
 #pragma unroll
-        for (int i = 0; i < 2 * W; ++i) sk[i] = child.k[i];
-        Q.c[dest * kQueue + q] = c;
-        lead_full = lane == leader && base + __popc(grp) >= 32;
+    for (int r = 0; r < kStage / 32; ++r) {
+        const uint32_t idx = r * 32 + lane;
+        d[r] = 0;
+        rk[r] = 0;
+        if (idx < n) {
+            d[r] = Q.dest[idx];
+            rk[r] = atomicAdd(&Q.cnt[d[r]], 1u);
+        }
     }
     __syncwarp();
-    uint32_t fl = __ballot_sync(0xFFFFFFFFu, lead_full);
-    while (fl) {
-        const int l = __ffs(fl) - 1;
-        fl &= fl - 1;
-        const int d = __shfl_sync(0xFFFFFFFFu, dest, l);
-        pb_flush<W>(S, st, Q, d, 32, lane);
+    {
+        // lanes < world: exclusive prefix of the counts (position in the sorted buffer) and the log reservation
+        const uint32_t cnt = lane < world ? Q.cnt[lane] : 0u;
+        uint32_t x = cnt;
+#pragma unroll
+        for (int o = 1; o < kPbMaxWorld; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane < world) {
+            Q.off[lane] = x - cnt;
+            unsigned long long pos = ~0ull;
+            if (cnt) {
+                pos = atomicAdd(&S.cursors[lane], (unsigned long long)cnt);
+                if (pos + cnt > (unsigned long long)log_cap) {
+                    atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_LOG_FULL);
+                    pos = ~0ull;
+                }
+            }
+            Q.gpos[lane] = pos;
+        }
     }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kStage / 32; ++r) {
+        const uint32_t idx = r * 32 + lane;
+        if (idx < n) {
+            const uint32_t t = Q.off[d[r]] + rk[r];
+#pragma unroll
+            for (int i = 0; i < W; ++i) Q.keys2[t * W + i] = Q.keys[idx * W + i];
+            Q.c2[t] = Q.c[idx];
+            Q.dest2[t] = d[r];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < kStage / 32; ++r) {
+        const uint32_t t = r * 32 + lane;
+        if (t < n) {
+            const uint32_t dd = Q.dest2[t];
+            const unsigned long long pos = Q.gpos[dd];
+            if (pos != ~0ull) {
+                const unsigned long long o = pos + (t - Q.off[dd]);
+                ulonglong2* dk = DB->keys[dd] + o * W;
+#pragma unroll
+                for (int i = 0; i < W; ++i) dk[i] = Q.keys2[t * W + i];
+                DB->c[dd][o] = Q.c2[t];
+            }
+        }
+    }
+    __syncwarp();
 }
 
 template <int W, bool TRUSTED>
 __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int warps_per_block) {
     const PbState* st = S.st;
     if (st->done) return;
-    extern __shared__ __align__(16) unsigned char pb_smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int world = S.world;
-    WarpQueues<W> Q;
-    {
-        unsigned char* p = pb_smem + (size_t)wib * queue_bytes_per_warp<W>(world);
-        Q.keys = reinterpret_cast<uint64_t*>(p);
-        p += (size_t)world * kQueue * 16 * W;
-        Q.c = reinterpret_cast<uint32_t*>(p);
-        p += (size_t)world * kQueue * 4;
-        Q.cnt = reinterpret_cast<uint32_t*>(p);
-        Q.head = Q.cnt + world;
+    __shared__ DestBase DB;
+    const int64_t l1 = st->l1, log_cap = st->log_cap;
+    if (threadIdx.x < world) {
+        char* base = S.peer[threadIdx.x];
+        DB.keys[threadIdx.x] = reinterpret_cast<ulonglong2*>(sh_keys(S, base)) + (int64_t)S.rank * log_cap * W;
+        DB.c[threadIdx.x] = sh_c(S, base) + (int64_t)S.rank * log_cap;
     }
-    if (lane < world) {
-        Q.cnt[lane] = 0;
-        Q.head[lane] = 0;
-    }
-    __syncwarp();
-    const int64_t l1 = st->l1;
+    __syncthreads();
+    Stage<W> Q(wib);
+    ulonglong2* sk = Q.keys;
+    uint32_t* sc = Q.c;
+    uint32_t* sd = Q.dest;
     const uint64_t head = (uint64_t)st->head;
     const int mrl = st->mrl;
     const bool cyc = st->cyclical != 0;
     const int min_len = st->min_len;
     const int64_t gw = (int64_t)blockIdx.x * warps_per_block + wib, nw = (int64_t)gridDim.x * warps_per_block;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t staged = 0;  // warp-uniform
     unsigned long long sent = 0;
     for (int64_t base = st->l0 + 32 * gw; base < l1; base += 32 * nw) {
         const int64_t j = base + lane;
@@ -394,41 +451,50 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
         split_key<W>(pk, p0, p1);
         const uint32_t cbase = (uint32_t)((pg - head) * 12);
         const uint64_t gbase = pg * 12;
-#pragma unroll
+#pragma unroll kPbUnroll
         for (int a = 0; a < 12; ++a) {
             Rel<2 * W> r0 = p0, r1 = p1;
-            int dest = -1;
+            bool emit = false;
             Key<W> child;
 #pragma unroll
             for (int i = 0; i < 2 * W; ++i) child.k[i] = 0;
             if (valid && a != back) {
                 bool co;
                 const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
-                const uint64_t gidc = gbase + a;
                 if (stt != ST_OK) {
-                    atomicMin(&S.ctrl_local[kCtrlErr], (unsigned long long)((gidc << 2) | (unsigned)stt));
+                    atomicMin(&S.ctrl_local[kCtrlErr], (unsigned long long)(((gbase + a) << 2) | (unsigned)stt));
                 } else {
                     const int L = r0.len + r1.len;
-                    if (L < min_len) atomicMin(&S.ctrl_local[kCtrlLen0 + L], (unsigned long long)gidc);
-                    if (L == 2) atomicMin(&S.ctrl_local[kCtrlSol], (unsigned long long)gidc);  // before the visited test
+                    if (L < min_len) atomicMin(&S.ctrl_local[kCtrlLen0 + L], (unsigned long long)(gbase + a));
+                    if (L == 2) atomicMin(&S.ctrl_local[kCtrlSol], (unsigned long long)(gbase + a));  // before the visited test
                     child = make_key<W>(r0, r1);
-                    if (!key_eq<W>(child, pk)) {
-                        dest = world > 1 ? pb_owner(pb_hash<W>(child), world) : 0;
-                        ++sent;
-                    }
+                    emit = !key_eq<W>(child, pk);
                 }
             }
-            pb_enqueue<W>(S, st, Q, dest, child, cbase + a, lane);
+            const uint32_t act = __ballot_sync(0xFFFFFFFFu, emit);
+            if (emit) {
+                const uint32_t q = staged + __popc(act & lt);
+#pragma unroll
+                for (int i = 0; i < W; ++i) sk[q * W + i] = make_ulonglong2(child.k[2 * i], child.k[2 * i + 1]);
+                sc[q] = cbase + a;
+                if (world > 1) sd[q] = (uint32_t)pb_owner<W>(child, world);
+            }
+            staged += __popc(act);
+            if (staged > kStage - 32) {
+                __syncwarp();
+                pb_flush<W>(S, &DB, wib, staged, lane, log_cap, world);
+                sent += staged;
+                staged = 0;
+            }
         }
     }
-    for (int d = 0; d < world; ++d) {
-        const uint32_t n = Q.cnt[d];
-        if (n) pb_flush<W>(S, st, Q, d, n, lane);
+    if (staged) {
+        __syncwarp();
+        pb_flush<W>(S, &DB, wib, staged, lane, log_cap, world);
+        sent += staged;
     }
     // the peer stores of this thread are performed before anything a later kernel publishes
     __threadfence_system();
-#pragma unroll
-    for (int off = 16; off; off >>= 1) sent += __shfl_xor_sync(0xFFFFFFFFu, sent, off);
     if (lane == 0 && sent) atomicAdd(&S.st->records_sent, sent);
 }
 
@@ -652,20 +718,34 @@ __global__ void __launch_bounds__(kScanT) pb_scan_sums_kernel(const PbShard S) {
     for (int64_t b = blockIdx.x; b < nblk; b += gridDim.x) {
         const bool combine = (int)(b % S.world) == S.rank;
         uint32_t sg = 0, sl = 0;
+        uint32_t g[kScanPer];
 #pragma unroll
         for (int k = 0; k < kScanPer; ++k) {
             const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
-            if (i < nwords) {
-                const uint32_t loc = __ldcg(mine + i);
-                sl += __popc(loc);
-                if (combine) {
-                    uint32_t g = loc;
-                    for (int r = 0; r < S.world; ++r)
-                        if (r != S.rank) g |= __ldcv(sh_bitmap(S, S.peer[r], st->buf) + i);
-                    for (int r = 0; r < S.world; ++r) sh_bmg(S, S.peer[r])[i] = g;
-                    sg += __popc(g);
+            g[k] = i < nwords ? __ldcg(mine + i) : 0u;
+            sl += __popc(g[k]);
+        }
+        if (combine) {
+            // all peer loads of the block are issued before the first one is consumed
+            for (int r = 0; r < S.world; ++r) {
+                if (r == S.rank) continue;
+                const uint32_t* pb = sh_bitmap(S, S.peer[r], st->buf);
+#pragma unroll
+                for (int k = 0; k < kScanPer; ++k) {
+                    const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
+                    if (i < nwords) g[k] |= __ldcv(pb + i);
                 }
             }
+            for (int r = 0; r < S.world; ++r) {
+                uint32_t* pg = sh_bmg(S, S.peer[r]);
+#pragma unroll
+                for (int k = 0; k < kScanPer; ++k) {
+                    const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
+                    if (i < nwords) pg[i] = g[k];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kScanPer; ++k) sg += __popc(g[k]);
         }
         block_sum2(sg, sl);
         if (threadIdx.x == 0) {
@@ -1148,7 +1228,7 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     cudaEventCreate(&b->ev1);
     for (auto& e : b->ring_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     // expand launch shape: as many warps per block as ~100 KB of staging allows
-    const size_t per_warp = b->W == 1 ? queue_bytes_per_warp<1>(world) : queue_bytes_per_warp<2>(world);
+    const size_t per_warp = b->W == 1 ? stage_bytes_per_warp<1>() : stage_bytes_per_warp<2>();
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb /= 2;
     b->expand_wpb = wpb;
@@ -1296,7 +1376,7 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         return ACS_OK;
     }
     const uint64_t h = pb_hash<W>(root);
-    const int owner = world > 1 ? pb_owner(h, world) : 0;
+    const int owner = world > 1 ? pb_owner<W>(root, world) : 0;
     bool same_device = true;
     for (int i = 0; i < n_local; ++i) same_device = same_device && sh[i]->device == b0->device;
     auto stream_of = [&](acs_pbfs* b) { return same_device ? b0->stream : b->stream; };
