@@ -1,4 +1,4 @@
-// ac_keys.cuh -- packed search-node keys shared by the device searches (bfs.cu, greedy.cu).
+// ac_keys.cuh -- packed search-node keys shared by the device searches (pbfs.cu, sbfs.cu, greedy.cu).
 //
 // A node key is the exact, canonical image of a padded int8 presentation: W 64-bit words per
 // relator (2-bit letter codes of ac_core.cuh) with the relator length in the top 6 bits of the

@@ -444,7 +444,9 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
             pg = (uint64_t)gj;
             if (TRUSTED && !cyc) {
                 // inverse pairs: r1<-r1 r0 / r1<-r1 r0^-1 (0,2); r0<-r0 r1^-1 / r0<-r0 r1 (1,3); conjugation by g / g^-1
-                if (pl >= 0) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
+                // (not for children of the root: a caller-supplied root need not be a normal form, and
+                // then the inverse move leads to its simplified form, a different state)
+                if (pl >= 16) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
             }
         }
         Rel<2 * W> p0, p1;
@@ -1648,6 +1650,52 @@ int acs_pbfs_set_timeout(acs_pbfs* b, double seconds) {
     if (!b || seconds <= 0) return ACS_ERR_INVALID;
     b->timeout_ns = (unsigned long long)(seconds * 1e9);
     return ACS_OK;
+}
+
+}  // extern "C"
+
+// ---- single-GPU search API (acs_bfs_*): the partitioned engine with a world of one ----------------
+struct acs_bfs {
+    acs_pbfs* shard = nullptr;
+};
+
+extern "C" {
+
+int acs_bfs_create(acs_ctx* /*ctx*/, int device, int mrl, int64_t max_nodes, int cyclical, acs_bfs** out) {
+    if (!out) return ACS_ERR_INVALID;
+    *out = nullptr;
+    acs_pbfs* p = nullptr;
+    const int rc = acs_pbfs_create(device, 0, 1, mrl, max_nodes, cyclical, 0, &p);
+    if (rc != ACS_OK) return rc;
+    acs_pbfs* arr[1] = {p};
+    const int rc2 = acs_pbfs_connect_local(arr, 1);
+    if (rc2 != ACS_OK) {
+        acs_pbfs_destroy(p);
+        return rc2;
+    }
+    acs_bfs* b = new acs_bfs();
+    b->shard = p;
+    *out = b;
+    return ACS_OK;
+}
+
+int acs_bfs_run(acs_bfs* b, const int8_t* h_presentation, int32_t* h_path, int path_cap, acs_search_result* res) {
+    if (!b || !b->shard || !h_presentation || !res) return ACS_ERR_INVALID;
+    acs_pbfs* arr[1] = {b->shard};
+    return acs_pbfs_run(arr, 1, h_presentation, h_path, path_cap, res);
+}
+
+int acs_bfs_visited(acs_bfs* b, int8_t* h_out, int64_t cap_rows, int64_t* n_out) {
+    if (!b || !b->shard || (!h_out && cap_rows > 0)) return ACS_ERR_INVALID;
+    // with one rank the local order IS the global (FIFO) order
+    std::vector<int64_t> gid((size_t)std::max<int64_t>(std::min<int64_t>(cap_rows, b->shard->h_final.n_local), 1));
+    return acs_pbfs_visited(b->shard, gid.data(), h_out, cap_rows, n_out);
+}
+
+void acs_bfs_destroy(acs_bfs* b) {
+    if (!b) return;
+    acs_pbfs_destroy(b->shard);
+    delete b;
 }
 
 }  // extern "C"

@@ -1,6 +1,6 @@
 """Breadth-first search of the AC graph -- drop-in for the reference's
 ``ac_solver/search/breadth_first.py`` (``bfs``), executed entirely on the GPU
-(csrc/bfs.cu): same return value, same visited set in the same order at any node budget,
+(csrc/pbfs.cu, the partitioned engine with a world of one): same return value, same visited set in the same order at any node budget,
 same console output.
 """
 

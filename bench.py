@@ -46,8 +46,9 @@ def parse_args():
     ap.add_argument("--mrl", type=int, default=36)
     ap.add_argument("--cpu-sample-rows", type=int, default=1 << 17)
     ap.add_argument("--skip-bfs", action="store_true")
-    ap.add_argument("--bfs-budget", type=int, default=100_000_000)
-    ap.add_argument("--bfs-timeout", type=float, default=90.0)
+    ap.add_argument("--bfs-budget", type=int, default=1_000_000_000, help="BASELINE.json configs[4]: 1e9 nodes")
+    ap.add_argument("--bfs-timeout", type=float, default=150.0)
+    ap.add_argument("--skip-python-baseline", action="store_true")
     return ap.parse_args()
 
 
@@ -145,6 +146,52 @@ def cpu_baseline(rows, mrl, seconds_target=12.0):
     }
 
 
+def _py_worker(job):
+    """One process of the pure-Python baseline: ACMove(cyclical=True) of the STAGED reference
+    (baseline/_ref, the reference's own modules) over a slice of rows for a fixed time."""
+    rows, actions, mrl, seconds = job
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    from ac_solver.envs.ac_moves import ACMove  # the reference's function, unmodified
+
+    n, t0, i = 0, time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        r = rows[i % len(rows)]
+        lens = [int(np.count_nonzero(r[:mrl])), int(np.count_nonzero(r[mrl:]))]
+        try:
+            ACMove(int(actions[i % len(rows)]), r, mrl, lens, cyclical=True)
+        except AssertionError:
+            pass  # the reference raises when a move empties a relator
+        n += 1
+        i += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline_python(rows, mrl, seconds=8.0):
+    """The reference's own pure-Python ACMove on every host core, bounded sample."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "ac_solver")):
+        return {"unavailable": "baseline/_ref not staged (run __graft_entry__.build() where /root/reference exists)"}
+    import multiprocessing as mp
+
+    from ac_solver_b200.synthetic import random_actions, random_presentations
+
+    cores = host_threads()
+    S = random_presentations(rows, mrl, seed=0)
+    A = random_actions(rows, seed=1)
+    per = max(1, rows // cores)
+    jobs = [(S[k * per:(k + 1) * per], A[k * per:(k + 1) * per], mrl, seconds) for k in range(cores) if len(S[k * per:(k + 1) * per])]
+    try:
+        with mp.get_context("spawn").Pool(len(jobs)) as pool:
+            out = pool.map(_py_worker, jobs)
+    except Exception as e:  # the baseline is auxiliary: never lose the headline line
+        return {"unavailable": repr(e)}
+    total = sum(n for n, _ in out)
+    dt = max(t for _, t in out)
+    return {"value": total / dt, "unit": "moves/s", "cores": len(jobs), "kind": "reference",
+            "per_core": total / dt / len(jobs),
+            "sample": f"the reference's own ACMove(cyclical=True) (baseline/_ref, pure Python) over the first {rows} "
+                      f"synthetic rows (mrl {mrl}), {len(jobs)} processes x {seconds:.0f} s"}
+
+
 def run_reference(args):
     rank, _, world = dist_env()
     if rank != 0:
@@ -157,7 +204,10 @@ def run_reference(args):
     A = random_actions(rows, seed=1)
     sc = np.zeros(rows, np.int32)
     threads = host_threads()  # torchrun pins OMP_NUM_THREADS=1: ask for every core explicitly
+    w0 = time.perf_counter()  # warm for >= 1.5 s: thread pool, page tables and caches in steady state
     for _ in range(max(args.warmup, 1)):
+        O.env_step_batch(S, A, sc, HORIZON, nthreads=threads)
+    while time.perf_counter() - w0 < 1.5:
         O.env_step_batch(S, A, sc, HORIZON, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -218,11 +268,11 @@ def run_b200(args):
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
-    def step(i):
+    def step(i, flags=FLAGS):
         b = i % nbuf
         rc = L.acs_env_step_batch(states[b].data_ptr(), actions[(i // nbuf + b) % nbuf].data_ptr(), reward.data_ptr(),
                                   done.data_ptr(), trunc.data_ptr(), stepc[b].data_ptr(), lens[b].data_ptr(), None,
-                                  err.data_ptr(), rows, mrl, HORIZON, FLAGS, sptr)
+                                  err.data_ptr(), rows, mrl, HORIZON, flags, sptr)
         if rc != 0:
             _lib.check(rc)
 
@@ -252,6 +302,58 @@ def run_b200(args):
         ms = float(t.item())
     barrier()
     n_bad = int(err[0].item())
+
+    # ---- the general variant (flags = 0: full validate + simplify of both relators, lengths recounted),
+    # what a caller gets from ac_moves_batch / a first step on caller-supplied states ----
+    gen_steps = max(20, min(args.steps // 4, 400))
+    for i in range(10):
+        step(i, 0)
+    barrier()
+    gv0, gv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gv0.record(stream)
+    for i in range(gen_steps):
+        step(10 + i, 0)
+    gv1.record(stream)
+    torch.cuda.synchronize()
+    ms_general = gv0.elapsed_time(gv1) / gen_steps
+    if dist is not None:
+        t = torch.tensor([ms_general], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_general = float(t.item())
+    barrier()
+
+    # ---- in-run parity: the first 131 072 rows of the batch, one step with each
+    # kernel variant, every output against the CPU oracle ----
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+
+        pn = min(rows, 1 << 17)
+        ps = np.ascontiguousarray(host_states[:pn])
+        pa = random_actions(pn, seed=1)
+        exp_state = ps.copy()
+        exp_sc = np.full(pn, HORIZON - 1, np.int32)  # the step reaches the horizon: truncated is exercised too
+        er, ed, et, el, es = O.env_step_batch(exp_state, pa, exp_sc, HORIZON, nthreads=host_threads())
+        mism = 0
+        for flags in sorted({FLAGS, 0}):
+            d_s = torch.from_numpy(ps.copy()).cuda()
+            d_a = torch.from_numpy(pa).cuda()
+            d_r = torch.zeros(pn, dtype=torch.int32, device="cuda")
+            d_d = torch.zeros(pn, dtype=torch.uint8, device="cuda")
+            d_t = torch.zeros(pn, dtype=torch.uint8, device="cuda")
+            d_c = torch.full((pn,), HORIZON - 1, dtype=torch.int32, device="cuda")
+            d_l = torch.stack([(d_s[:, :mrl] != 0).sum(1), (d_s[:, mrl:] != 0).sum(1)], dim=1).to(torch.uint8).contiguous()
+            d_st = torch.zeros(pn, dtype=torch.uint8, device="cuda")
+            _lib.check(L.acs_env_step_batch(d_s.data_ptr(), d_a.data_ptr(), d_r.data_ptr(), d_d.data_ptr(), d_t.data_ptr(),
+                                            d_c.data_ptr(), d_l.data_ptr(), d_st.data_ptr(), None, pn, mrl, HORIZON, flags, sptr))
+            torch.cuda.synchronize()
+            ok = es == 0
+            bad = (d_s.cpu().numpy() != exp_state).any(axis=1) | (d_st.cpu().numpy() != es)
+            bad |= ok & ((d_r.cpu().numpy() != er) | (d_d.cpu().numpy() != ed) | (d_t.cpu().numpy() != et)
+                         | (d_c.cpu().numpy() != exp_sc) | (d_l.cpu().numpy() != el).any(axis=1))
+            mism += int(bad.sum())
+        parity = {"rows": pn, "variants_checked": sorted({FLAGS, 0}), "mismatches": mism, "rows_raising": int((es != 0).sum()),
+                  "checked": "next state, reward, done, truncated, step counter, lengths, per-row status vs the CPU oracle"}
 
     # ---- e2e: the vector-env call with HOST buffers (actions in; obs, reward, flags out) ----
     e2e_steps = max(3, min(args.steps, 30))
@@ -293,6 +395,9 @@ def run_b200(args):
         achieved = algo_bytes * rows / (ms_per_step * 1e-3) / 1e9
         # the CPU baseline is timed on rank 0 at N=1 only (it would stall the other ranks)
         cpu = cpu_baseline(args.cpu_sample_rows, mrl) if world == 1 else None
+        cpu_py = cpu_baseline_python(args.cpu_sample_rows, mrl) if (world == 1 and not args.skip_python_baseline) else None
+        traffic, traffic_src = ncu_traffic()
+        achieved_general = algo_bytes * rows / (ms_general * 1e-3) / 1e9
         line = {
             "metric": "AC moves/sec (batched env steps)",
             "value": moves_per_s,
@@ -317,13 +422,21 @@ def run_b200(args):
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic_bytes(), "peak_source": peak_src, "algorithmic_bytes_per_move": 4 * mrl + 6,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_move": 4 * mrl + 6,
                 "kernel": ("acs::ac_step_words_kernel<NW=9, TRUSTED=%s, LENS=%s, TR=128>"
                            % (bool(FLAGS & 2), bool(FLAGS & 4))) if mrl == 36 else "acs::ac_step_*_kernel",
                 "kernel_flags": FLAGS,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
             },
+            "roofline_general": {
+                "bound": "hbm", "achieved": achieved_general, "peak": peak, "unit": "GB/s", "frac": achieved_general / peak,
+                "ms_per_step": ms_general, "steps": gen_steps, "kernel_flags": 0,
+                "kernel": "the general variant: reference's full validate + simplify of both relators, lengths recounted",
+            },
+            "parity": parity,
             "cpu_baseline": cpu,
+            "cpu_baseline_python": cpu_py,
             "e2e": {
                 "value": world * rows * e2e_steps / e2e_s,
                 "unit": "moves/s",
@@ -332,7 +445,7 @@ def run_b200(args):
                 "steps": e2e_steps,
                 "api": "acs_env_step_host: pinned host actions in; host observations, rewards, done, truncated out",
             },
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps,  # kernels of the timed region (one ac_step kernel per step)
             "clocks": sampler.summary(),
         }
     else:
@@ -372,67 +485,129 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the latest committed `ncu --set full` capture of
-    the step kernel (profiles/k1_step_r1_ncu_summary.json; cold-cache, the write-back of the last
-    tiles is still in L2 when the capture ends, so it reads below the algorithmic bytes)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "k1_step_r1_ncu_summary.json")) as f:
-            d = json.load(f)
-        m = d[sorted(d)[-1]]
-        return (float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])) * 1e6
-    except Exception:
-        return None
+def ncu_traffic():
+    """DRAM bytes per launch of the step kernel from the latest committed ncu capture under
+    profiles/ (dram__bytes_read.sum + dram__bytes_write.sum), with its provenance.  A single
+    profiled launch under-counts writes still resident in L2 when the capture ends, so the
+    round-2 summary averages >= 8 back-to-back launches (profiles/k1_step_r2_ncu_summary.json)."""
+    for name in ("k1_step_r2_ncu_summary.json", "k1_step_r1_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            if "traffic_bytes_per_launch" in d:
+                return float(d["traffic_bytes_per_launch"]), d.get("source", name)
+            m = d[sorted(d)[-1]]
+            return ((float(m["dram__bytes_read.sum"]) + float(m["dram__bytes_write.sum"])) * 1e6,
+                    f"profiles/{name} (single cold-cache launch; last tiles' write-back still in L2)")
+        except Exception:
+            continue
+    return None, None
+
+
+AK3 = np.array([1, 1, 1, -2, -2, -2, -2] + [0] * 17 + [1, 2, 1, -2, -1, -2] + [0] * 18, np.int8)
+RANDOM_REQUEST_PEAK = 37.0e9  # measured on B200: scripts/microbench/random_access.cu (profiles/random_access_r2.jsonl)
 
 
 def bench_bfs(args, world=1, dist=None):
-    """Secondary metric: BFS nodes expanded / s on AK(3), mrl 24 (BASELINE.json configs[4]).
-    One GPU: the single-device search (csrc/bfs.cu).  Several GPUs: the hash-partitioned search
-    with an NCCL all-to-all per chunk (search/sharded.py), same total budget (strong scaling)."""
-    ak3 = np.array([1, 1, 1, -2, -2, -2, -2] + [0] * 17 + [1, 2, 1, -2, -1, -2] + [0] * 18, np.int8)
-    if world > 1:
-        import contextlib
-        import io
+    """Secondary metric: BFS nodes expanded / s on AK(3), mrl 24, budget 1e9 (BASELINE.json
+    configs[4]) with the native hash-partitioned search (csrc/pbfs.cu): one GPU = a world of one;
+    N GPUs = one process per GPU, newly generated states stored straight into the owner's inbox
+    over NVLink (cudaIpc peer memory), same total budget (strong scaling).  Also, in the same run:
+    bit-exact parity of a 1e6-budget search on the same ranks against the CPU oracle, and the
+    roofline of the search (algorithmic bytes of SURVEY 8d with the measured u)."""
+    import torch
 
-        import torch
-        from ac_solver_b200.search.sharded import bfs_sharded
+    from ac_solver_b200.search.partitioned import PartitionedBfs
 
-        with contextlib.redirect_stdout(io.StringIO()):
-            bfs_sharded(ak3, 1_000_000)  # warm
+    rank = dist.get_rank() if dist is not None else 0
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
             dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            solved, path, info = bfs_sharded(ak3, args.bfs_budget)
-            torch.cuda.synchronize()
-            dist.barrier()
+
+    # ---- parity on the same ranks: visited ARRAY in insertion order, path, counters ----
+    parity_budget = 1_000_000
+    with PartitionedBfs(24, parity_budget) as eng:
+        solved, path, info = eng.run(AK3, want_visited=True)
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+
+        es, ep, ei = O.bfs(AK3, parity_budget, want_visited=True)
+        same = (solved, path) == (es, ep) and all(info[k] == ei[k] for k in
+                                                    ("n_visited", "n_expanded", "n_moves", "budget_hit", "minlen_log"))
+        vis_ok = info["visited"].shape == ei["visited"].shape and bool(np.array_equal(info["visited"], ei["visited"]))
+        parity = {"budget": parity_budget, "world": world, "visited_rows_compared": int(ei["n_visited"]),
+                  "mismatches": 0 if (same and vis_ok) else int((info["visited"][: len(ei["visited"])] != ei["visited"][: len(info["visited"])]).any(axis=1).sum()) + (0 if same else 1),
+                  "checked": "result, path, counters, minimal-length log and the visited array in insertion order vs the CPU oracle"}
+    # ---- timed search ----
+    with PartitionedBfs(24, args.bfs_budget) as eng:
+        eng.run(AK3)  # warm-up: first touch of the buffers, peer mappings
+        sync()
+        t0 = time.perf_counter()
+        solved, path, info = eng.run(AK3)
+        sync()
         wall = time.perf_counter() - t0
-        return {
-            "metric": "BFS nodes expanded/sec", "nodes_expanded": info["n_expanded"], "visited": info["n_visited"],
-            "workload": f"sharded bfs AK(3) mrl 24 budget {args.bfs_budget}, {world} GPUs, hash-partitioned, "
-                        "NCCL all-to-all per chunk",
-            "levels": info["n_levels"], "expanded_per_s_wall": info["n_expanded"] / wall, "seconds_wall": wall,
-        }
-    from ac_solver_b200.search.breadth_first import bfs_device
-
-    bfs_device(ak3, 100000)  # warm
-    t0 = time.perf_counter()
-    solved, path, info = bfs_device(ak3, args.bfs_budget)
-    wall = time.perf_counter() - t0
-    # CPU baseline beside it (BASELINE.md section 3): the C oracle's sequential bfs on one core,
-    # bounded to a 2e6-node budget of the same search
-    from oracle import oracle as O
-
-    c0 = time.perf_counter()
-    _, _, cinfo = O.bfs(ak3, 2_000_000)
-    cpu_s = time.perf_counter() - c0
-    return {
-        "metric": "BFS nodes expanded/sec", "workload": f"bfs AK(3) mrl 24 budget {args.bfs_budget}, 1 GPU",
-        "nodes_expanded": info["n_expanded"], "visited": info["n_visited"], "levels": info["n_levels"],
-        "expanded_per_s_device": info["n_expanded"] / max(info["seconds_device"], 1e-9),
-        "expanded_per_s_wall": info["n_expanded"] / wall, "seconds_wall": wall,
-        "cpu_baseline": {"value": cinfo["n_expanded"] / cpu_s, "unit": "nodes expanded/s", "cores": 1, "kind": "port",
-                         "sample": "C oracle bfs, same presentation, budget 2e6 (sequential algorithm, one core)"},
+    t = torch.tensor([wall, info["seconds_device"]], device="cuda", dtype=torch.float64)
+    recs = torch.tensor([float(info["records_sent"][0]), float(info["records_recv"][0])], device="cuda", dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(recs, op=dist.ReduceOp.SUM)
+    wall, dev_s = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    expanded, visited = info["n_expanded"], info["n_visited"]
+    records = float(recs[0])
+    u = visited / max(expanded, 1)
+    peak, peak_src = measured_peak_gbs()
+    # SURVEY 8d: parent read 2*mrl + 12 probes x 16 B key + u x (key insert 16 + frontier append 2*mrl + parent record 8)
+    bytes_per_exp = 2 * 24 + 12 * 16 + u * (16 + 2 * 24 + 8)
+    achieved = bytes_per_exp * expanded / dev_s / 1e9
+    # the insert kernel is bound by random memory REQUESTS, not bytes: one bucket load per record, one log-key
+    # load per duplicate, one CAS per new state (an atomic costs ~1.85 loads at the measured 20 G atomics/s)
+    dup = max(records - visited, 0.0)
+    req_per_exp = (records + dup + 1.85 * visited) / max(expanded, 1)
+    out = {
+        "metric": "BFS nodes expanded/sec",
+        "workload": f"bfs AK(3) mrl 24 budget {args.bfs_budget} (BASELINE.json configs[4]), {world} GPU(s), hash-partitioned, "
+                    "native driver (csrc/pbfs.cu): expansion fused with the NVLink exchange (peer stores), no host syncs per chunk",
+        "n_gpus": world, "nodes_expanded": expanded, "visited": visited, "levels": info["n_levels"], "chunks": info["chunks"],
+        "expanded_per_s_device": expanded / dev_s, "visited_per_s_device": visited / dev_s, "seconds_device": dev_s,
+        "expanded_per_s_wall": expanded / wall, "seconds_wall": wall, "scaling": "strong",
+        "new_states_per_expansion_u": u, "records_per_expansion": records / max(expanded, 1),
+        "parity": parity,
+        "roofline": {"bound": "hbm", "bytes_per_expansion": bytes_per_exp, "achieved": achieved, "peak": peak * world,
+                     "unit": "GB/s", "frac": achieved / (peak * world), "traffic": bfs_traffic(world), "peak_source": peak_src,
+                     "note": "algorithmic bytes of SURVEY 8d with the measured u; the search is bound by random-access "
+                             "REQUESTS (request_roofline), not by bytes"},
+        "request_roofline": {"bound": "random 32-byte memory requests", "requests_per_expansion": req_per_exp,
+                             "achieved": req_per_exp * expanded / dev_s / 1e9, "peak": RANDOM_REQUEST_PEAK * world / 1e9,
+                             "unit": "G requests/s", "frac": req_per_exp * expanded / dev_s / (RANDOM_REQUEST_PEAK * world),
+                             "peak_source": "measured, scripts/microbench/random_access.cu on B200 (profiles/random_access_r2.jsonl)"},
+        "nvlink": None if world == 1 else {
+            "bytes_sent_per_expansion": records * (world - 1) / world * 20 / max(expanded, 1),
+            "GBps_per_gpu": records * (world - 1) / world * 20 / world / dev_s / 1e9, "peak_GBps_per_gpu_per_direction": 900.0},
     }
+    if world == 1:
+        from oracle import oracle as O
+
+        c0 = time.perf_counter()
+        _, _, cinfo = O.bfs(AK3, 2_000_000)
+        cpu_s = time.perf_counter() - c0
+        out["cpu_baseline"] = {"value": cinfo["n_expanded"] / cpu_s, "unit": "nodes expanded/s", "cores": 1, "kind": "port",
+                               "sample": "C oracle bfs, same presentation, budget 2e6 (sequential algorithm, one core)"}
+    return out
+
+
+def bfs_traffic(world):
+    """DRAM bytes per expansion from the committed ncu launch list of the 1-GPU search (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pbfs_r2_ncu_summary.json")) as f:
+            d = json.load(f)
+        return {"dram_bytes_per_expansion": d["dram_bytes_per_expansion"], "source": d["source"]} if world == 1 else None
+    except Exception:
+        return None
 
 
 def main():
