@@ -67,6 +67,7 @@ struct acs_ctx {
     Scratch scratch[kStreams];
     unsigned long long* d_err = nullptr;  // {count, min row}
     unsigned long long* h_err = nullptr;  // pinned mirror
+    std::mutex mu;  // the *_host calls share streams and scratch: one caller at a time per context
 };
 
 extern "C" {
@@ -244,6 +245,7 @@ int acs_generic_batch(int op, const int8_t* d_in, const uint8_t* d_action, int8_
 int acs_moves_batch_host(acs_ctx* c, const int8_t* h_in, const uint8_t* h_action, int8_t* h_out, uint8_t* h_lens,
                          uint8_t* h_status, int64_t n, int mrl, int flags) {
     if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    std::lock_guard<std::mutex> lock(c->mu);
     if (n < 0 || (n > 0 && (!h_in || !h_action || !h_out))) return fail(ACS_ERR_INVALID, "null buffer");
     if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
     ACS_CUDA(cudaSetDevice(c->device));
@@ -280,6 +282,7 @@ int acs_env_step_host(acs_ctx* c, int8_t* d_state, int32_t* d_step_count, const 
                       int32_t* h_reward, uint8_t* h_done, uint8_t* h_truncated, int64_t n, int mrl, int horizon,
                       int flags, int64_t* n_bad) {
     if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    std::lock_guard<std::mutex> lock(c->mu);
     if (n < 0 || (n > 0 && (!d_state || !d_step_count || !h_action || !h_reward || !h_done || !h_truncated)))
         return fail(ACS_ERR_INVALID, "null buffer");
     if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
@@ -321,6 +324,7 @@ int acs_env_step_host(acs_ctx* c, int8_t* d_state, int32_t* d_step_count, const 
 
 int acs_validate_batch_host(acs_ctx* c, const int8_t* h_in, uint8_t* h_flags, int64_t n, int mrl) {
     if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    std::lock_guard<std::mutex> lock(c->mu);
     if (n < 0 || (n > 0 && (!h_in || !h_flags)) || mrl < 1) return fail(ACS_ERR_INVALID, "bad argument");
     if (n == 0) return ACS_OK;
     ACS_CUDA(cudaSetDevice(c->device));
@@ -341,6 +345,7 @@ int acs_validate_batch_host(acs_ctx* c, const int8_t* h_in, uint8_t* h_flags, in
 int acs_generic_host(acs_ctx* c, int op, const int8_t* h_in, const uint8_t* h_action, int8_t* h_out, int32_t* h_aux,
                      uint8_t* h_status, int64_t n, int width, int i, int j, int sign, int cyclical) {
     if (!c) return fail(ACS_ERR_INVALID, "ctx is null");
+    std::lock_guard<std::mutex> lock(c->mu);
     if (n < 0 || (n > 0 && (!h_in || !h_out || !h_aux || !h_status))) return fail(ACS_ERR_INVALID, "null buffer");
     if (n == 0) return ACS_OK;
     ACS_CUDA(cudaSetDevice(c->device));

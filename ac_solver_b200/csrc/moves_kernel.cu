@@ -89,7 +89,12 @@ __device__ __forceinline__ void write_row_outputs(const StepParams& P, int64_t r
             atomicAdd((unsigned long long*)&P.err[0], 1ull);
             atomicMin((unsigned long long*)&P.err[1], (unsigned long long)row);
         }
-        return;  // the reference raised: state, counters and rewards stay untouched
+        if (P.reward) {  // the reference raised: the state and the step counter stay untouched; the step's
+            P.reward[row] = 0;  // outputs are cleared so that a stale done/truncated cannot trigger an auto-reset
+            P.done[row] = 0;
+            P.truncated[row] = 0;
+        }
+        return;
     }
     if (P.status) P.status[row] = 0;
     if (P.lens) reinterpret_cast<uchar2*>(P.lens)[row] = make_uchar2((uint8_t)o.len0, (uint8_t)o.len1);
@@ -326,7 +331,12 @@ __global__ void __launch_bounds__(TR, (TR <= 128 ? 8 : 4)) ac_step_words_kernel(
                 atomicAdd((unsigned long long*)&P.err[0], 1ull);
                 atomicMin((unsigned long long*)&P.err[1], (unsigned long long)row);
             }
-        } else {  // a raising row keeps its state, counters and rewards untouched
+            if (P.reward) {  // cleared, so that a stale done/truncated cannot trigger an auto-reset
+                P.reward[row] = 0;
+                P.done[row] = 0;
+                P.truncated[row] = 0;
+            }
+        } else {  // (a raising row keeps its state and step counter)
             if (P.status) P.status[row] = 0;
             if (P.lens) reinterpret_cast<uchar2*>(P.lens)[row] = make_uchar2((uint8_t)l0, (uint8_t)l1);
             if (P.reward) {  // ac_env.py:101-105

@@ -384,6 +384,16 @@ def run_b200(args):
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    # what the PCIe link gives a plain pinned device->host copy of the same observation buffer on this box:
+    # the e2e call moves 78 B per move to the host, so this bandwidth bounds it
+    torch.cuda.synchronize()
+    d2h_t = []
+    for _ in range(5):
+        c0 = time.perf_counter()
+        h_obs.copy_(states[0], non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_t.append(time.perf_counter() - c0)
+    d2h_gbps = rows * rowb / min(d2h_t) / 1e9
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -444,6 +454,9 @@ def run_b200(args):
                 "d2h_bytes_per_step": rows * (rowb + 4 + 1 + 1),
                 "steps": e2e_steps,
                 "api": "acs_env_step_host: pinned host actions in; host observations, rewards, done, truncated out",
+                "d2h_GBps_achieved": rows * (rowb + 6) * e2e_steps / e2e_s / 1e9,
+                "pinned_d2h_GBps_measured": d2h_gbps,
+                "frac_of_pinned_d2h": rows * (rowb + 6) * e2e_steps / e2e_s / 1e9 / d2h_gbps,
             },
             "gpu_launches": args.steps,  # kernels of the timed region (one ac_step kernel per step)
             "clocks": sampler.summary(),

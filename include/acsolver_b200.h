@@ -22,7 +22,9 @@
  *     ACS_ROW_OK, ACS_ROW_ASSERT (AssertionError, envs/utils.py:261-263) or
  *     ACS_ROW_INDEX (IndexError, envs/ac_moves.py:119).  Such rows are left unchanged.
  *   - The caller owns every buffer it passes.  The library owns only what *_create
- *     returns.  No global mutable state; a context may be used by one thread at a time.
+ *     returns.  No global mutable state.  The *_host calls of one context share its streams and
+ *     scratch buffers and are serialised by a mutex inside the context: they are thread-safe but do
+ *     not overlap; use one context per thread for concurrency.
  *   - The batched packed kernels require rows that are zero right-padded over the
  *     alphabet {+-1,+-2} (check once with acs_validate_batch); words need not be reduced
  *     and relators may be empty.  The generic kernels accept any int8 letters.
