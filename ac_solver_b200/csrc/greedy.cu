@@ -22,6 +22,8 @@
 //           reference's insertion order; then pushed (sift-up, <= 4 levels).
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -43,6 +45,7 @@ struct GreedyRec {  // per-search result record (device -> host)
     uint64_t n_nodes, n_expanded, n_moves, heap_left;
     uint64_t final_node;
     int32_t final_action, final_len;
+    int32_t rounds, engine;  // bucket rounds executed; 1 = bucket kernel, 2 = heap kernel (fallback or forced)
     int32_t minlen_log[128];
 };
 
@@ -56,6 +59,7 @@ struct GreedyArgs {
     GreedyRec* rec;    // [S]
     uint64_t cap, tcap, budget;
     int n_search, mrl, cyclical;
+    int fallback_only;  // run only the searches the bucket kernel handed back (status kGbFallback)
 };
 
 // signed order of the letters: -2 < -1 < +1 < +2  <->  codes 2 < 3 < 1 < 0
@@ -120,6 +124,7 @@ template <int W>
 __global__ void __launch_bounds__(32) greedy_kernel(const GreedyArgs A) {
     const int sidx = blockIdx.x;
     if (sidx >= A.n_search) return;
+    if (A.fallback_only && A.rec[sidx].status != 99) return;
     const int lane = threadIdx.x;
     uint64_t* keys = A.keys + (uint64_t)sidx * A.cap * 2 * W;
     uint64_t* parent = A.parent + (uint64_t)sidx * A.cap;
@@ -343,8 +348,14 @@ __global__ void __launch_bounds__(32) greedy_kernel(const GreedyArgs A) {
         rec->final_node = cur;
         rec->final_action = solved ? final_action : 11;
         rec->final_len = final_len;
+        rec->rounds = 0;
+        rec->engine = 2;
     }
 }
+
+}  // namespace acs
+#include "greedy_bucket.cuh"
+namespace acs {
 
 // path of every search: chain of its final node, then (final_action, final_len)
 template <int W>
@@ -389,6 +400,9 @@ struct acs_greedy {
     uint64_t *keys = nullptr, *parent = nullptr, *heap = nullptr, *table = nullptr, *roots = nullptr;
     uint32_t* depth = nullptr;
     GreedyRec* rec = nullptr;
+    GbArgs gb{};  // pools of the bucket kernel
+    bool use_bucket = true;
+    int n_fallback = 0;
     int32_t *d_paths = nullptr, *d_path_len = nullptr;
     int path_cap = 0;
     std::vector<GreedyRec> h_rec;
@@ -422,6 +436,12 @@ extern "C" void acs_greedy_destroy(acs_greedy* g) {
     cudaFree(g->roots);
     cudaFree(g->depth);
     cudaFree(g->rec);
+    cudaFree(g->gb.segs);
+    cudaFree(g->gb.sortbuf);
+    cudaFree(g->gb.cand_key);
+    cudaFree(g->gb.cand_meta);
+    cudaFree(g->gb.cand_slot);
+    cudaFree(g->gb.round_tab);
     cudaFree(g->d_paths);
     cudaFree(g->d_path_len);
     delete g;
@@ -481,6 +501,20 @@ extern "C" int acs_greedy_create(int device, int n_search, int mrl, int64_t max_
     GR_ALLOC(g->rec, S * sizeof(GreedyRec));
     GR_ALLOC(g->d_paths, S * (size_t)path_cap * 2 * sizeof(int32_t));
     GR_ALLOC(g->d_path_len, S * sizeof(int32_t));
+    {
+        const char* e = std::getenv("ACS_GREEDY_KERNEL");  // "heap" forces the one-warp-per-search kernel
+        g->use_bucket = !(e && std::string(e) == "heap");
+    }
+    if (g->use_bucket) {
+        GR_ALLOC(g->gb.segs, S * (size_t)kGbSegPool * sizeof(GbSeg));
+        GR_ALLOC(g->gb.sortbuf, S * (size_t)kGbSortCap * (2 * g->W + 2) * sizeof(uint64_t));
+        GR_ALLOC(g->gb.cand_key, S * (size_t)kGbCand * 2 * g->W * sizeof(uint64_t));
+        GR_ALLOC(g->gb.cand_meta, S * (size_t)kGbCand * sizeof(uint32_t));
+        GR_ALLOC(g->gb.cand_slot, S * (size_t)kGbCand * sizeof(uint32_t));
+        GR_ALLOC(g->gb.round_tab, S * (size_t)kGbRoundSlots * sizeof(uint64_t));
+        g->gb.frontier = reinterpret_cast<uint32_t*>(g->heap);  // the heap pool doubles as the frontier array
+        g->gb.fcap = 2 * g->cap;
+    }
 #undef GR_ALLOC
     g->h_rec.resize(S);
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(ACS_ERR_CUDA);
@@ -536,9 +570,46 @@ int greedy_run_impl(acs_greedy* g, const int8_t* h_pres, int32_t* h_paths, acs_s
     A.n_search = S;
     A.mrl = g->mrl;
     A.cyclical = g->cyclical;
+    A.fallback_only = 0;
     GR_CUDA(cudaEventRecord(g->ev0, st));
-    greedy_kernel<W><<<S, 32, 0, st>>>(A);
-    GR_CUDA(cudaGetLastError());
+    g->n_fallback = 0;
+    if (g->use_bucket) {
+        // pass 1: small bucket directory (several CTAs per SM); pass 2: the searches that outgrew it, with a
+        // large directory (one CTA per SM); whatever still does not fit is re-run by the heap kernel
+        auto smem_for = [](int buckets) { return ((sizeof(GbShared) + 15) / 16) * 16 + (size_t)buckets * sizeof(GbBucket); };
+        GR_CUDA(cudaFuncSetAttribute(greedy_bucket_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem_for(kGbBuckets2)));
+        const bool debug = std::getenv("ACS_GREEDY_DEBUG") != nullptr;
+        for (int pass = 0; pass < 2; ++pass) {
+            g->gb.max_buckets = pass == 0 ? kGbBuckets1 : kGbBuckets2;
+            g->gb.retry_only = pass;
+            cudaEvent_t e0 = pass == 0 ? g->ev0 : g->ev1;
+            if (pass) GR_CUDA(cudaEventRecord(e0, st));
+            greedy_bucket_kernel<W><<<S, kGbThreads, smem_for(g->gb.max_buckets), st>>>(A, g->gb);
+            GR_CUDA(cudaGetLastError());
+            GR_CUDA(cudaMemcpyAsync(g->h_rec.data(), g->rec, (size_t)S * sizeof(GreedyRec), cudaMemcpyDeviceToHost, st));
+            GR_CUDA(cudaStreamSynchronize(st));
+            g->n_fallback = 0;
+            for (int s = 0; s < S; ++s)
+                if (g->h_rec[s].status == kGbFallback) {
+                    ++g->n_fallback;
+                    if (debug)
+                        std::fprintf(stderr, "greedy: pass %d, search %d handed back (reason %d, %llu nodes)\n", pass, s,
+                                     -g->h_rec[s].rounds, (unsigned long long)g->h_rec[s].n_nodes);
+                    GR_CUDA(cudaMemsetAsync(g->table + (size_t)s * g->tcap, 0, g->tcap * sizeof(uint64_t), st));
+                }
+            if (debug) std::fprintf(stderr, "greedy: bucket pass %d, %d searches, mrl %d: %d handed back\n", pass, S, g->mrl, g->n_fallback);
+            if (!g->n_fallback) break;
+        }
+        if (g->n_fallback) {
+            A.fallback_only = 1;
+            greedy_kernel<W><<<S, 32, 0, st>>>(A);
+            GR_CUDA(cudaGetLastError());
+        }
+    } else {
+        greedy_kernel<W><<<S, 32, 0, st>>>(A);
+        GR_CUDA(cudaGetLastError());
+    }
     greedy_path_kernel<W><<<(S + 63) / 64, 64, 0, st>>>(A, g->d_paths, g->path_cap, g->d_path_len);
     GR_CUDA(cudaGetLastError());
     GR_CUDA(cudaEventRecord(g->ev1, st));
@@ -563,7 +634,7 @@ int greedy_run_impl(acs_greedy* g, const int8_t* h_pres, int32_t* h_paths, acs_s
         o.n_expanded = (int64_t)r.n_expanded;
         o.n_moves = (int64_t)r.n_moves;
         o.frontier_left = (int64_t)r.heap_left;
-        o.n_levels = 0;
+        o.n_levels = r.engine == 1 ? r.rounds : -1;  // bucket rounds; -1 = served by the heap kernel
         o.n_minlen = r.n_minlen;
         std::memcpy(o.minlen_log, r.minlen_log, sizeof(o.minlen_log));
         o.seconds_device = ms * 1e-3;

@@ -1,6 +1,7 @@
 """Greedy (best-first) search of the AC graph -- drop-in for the reference's
 ``ac_solver/search/greedy.py`` (``greedy_search``), executed on the GPU (csrc/greedy.cu), plus
-the batched form used for the Miller-Schupp sweep (one warp per presentation, one launch).
+the batched form used for the Miller-Schupp sweep (one CTA per presentation, one launch: a whole
+(length, depth) bucket of the frontier is expanded per round, csrc/greedy_bucket.cuh).
 """
 
 from __future__ import annotations
@@ -49,6 +50,8 @@ def greedy_search_batch(presentations, max_nodes_to_explore=10000, cyclically_re
                 "frontier_left": int(r.frontier_left), "budget_hit": bool(r.budget_hit), "status": int(r.status),
                 "minlen_log": [int(r.minlen_log[i]) for i in range(r.n_minlen)],
                 "seconds_device": float(r.seconds_device),
+                # bucket rounds of the CTA-per-search kernel; -1: served by the one-warp heap kernel
+                "rounds": int(r.n_levels),
             }
             if r.path_len > path_cap:
                 raise _lib.AcsError(f"greedy path of {r.path_len} entries exceeds path_cap={path_cap}")

@@ -69,7 +69,7 @@ def main():
         for part, out in pool.map(run_group, parts):
             dev_s = max(dev_s, out[0][2]["seconds_device"])
             for k, (solved, path, info) in zip(part, out):
-                mine[k] = (solved, path, info["n_visited"], info["n_expanded"])
+                mine[k] = (solved, path, info["n_visited"], info["n_expanded"], info["rounds"])
     print(f"rank {rank}: {len(parts)} groups done", file=sys.stderr, flush=True)
     if dist is not None:
         gathered = [None] * world if rank == 0 else None
@@ -83,7 +83,7 @@ def main():
         n_solved = n_path_ok = visited = expanded = 0
         wrong = []
         for k in range(len(ms["mrl"])):
-            solved, path, nv, ne = mine[k]
+            solved, path, nv, ne, rounds = mine[k]
             visited += nv
             expanded += ne
             n_solved += solved
@@ -98,15 +98,29 @@ def main():
         line = {"config": "greedy_search over 1190 Miller-Schupp presentations", "budget": args.budget, "n_gpus": world,
                 "solved": n_solved, "stored_paths_reproduced": n_path_ok, "mismatching_rows": wrong[:20],
                 "visited_total": visited, "expanded_total": expanded, "seconds_wall": wall,
-                "seconds_device_max_rank": dev_s, "visited_per_s_wall": visited / wall}
+                "seconds_device_max_rank": dev_s, "visited_per_s_wall": visited / wall,
+                "heap_kernel_fallbacks": sum(1 for v in mine.values() if v[4] < 0),
+                "max_bucket_rounds": max(v[4] for v in mine.values())}
         if not args.no_cpu_baseline:
-            # CPU baseline beside it: the C oracle on sampled unsolved rows, one core
+            # CPU baseline beside it: the C oracle (a port, far faster than the
+            # reference's Python) on ALL host cores, one search per thread (ctypes releases the GIL), over a
+            # sample of unsolved rows at the full budget; the sweep time is extrapolated from it.
+            from concurrent.futures import ThreadPoolExecutor as TP
+
             from oracle import oracle as O
 
+            cores = max(1, len(os.sched_getaffinity(0)))
+            unsolved = [k for k in range(533, len(ms["mrl"]))]
+            sample = unsolved[:: max(1, len(unsolved) // (2 * cores))][: 2 * cores]
             c0 = time.perf_counter()
-            cpu_visited = sum(O.greedy_search(row(k), 100_000)[2]["n_visited"] for k in (533, 700, 900, 1189))
-            line["cpu_baseline"] = {"value": cpu_visited / (time.perf_counter() - c0), "unit": "visited/s", "cores": 1,
-                                    "kind": "port", "sample": "C oracle greedy, 4 unsolved rows at budget 1e5"}
+            with TP(max_workers=cores) as tp:
+                cv = list(tp.map(lambda k: O.greedy_search(row(k), args.budget)[2]["n_visited"], sample))
+            cs = time.perf_counter() - c0
+            line["cpu_baseline"] = {"value": sum(cv) / cs, "unit": "visited/s", "cores": cores, "kind": "port",
+                                    "sample": f"C oracle greedy, {len(sample)} unsolved rows at budget {args.budget}, "
+                                              f"{cores} threads: {cs:.1f} s",
+                                    "sweep_seconds_extrapolated": cs / len(sample) * len(unsolved),
+                                    "speedup_vs_allcore_port": (cs / len(sample) * len(unsolved)) / wall}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
