@@ -53,8 +53,11 @@ def greedy_search_batch(presentations, max_nodes_to_explore=10000, cyclically_re
                 # bucket rounds of the CTA-per-search kernel; -1: served by the one-warp heap kernel
                 "rounds": int(r.n_levels),
             }
-            if r.path_len > path_cap:
-                raise _lib.AcsError(f"greedy path of {r.path_len} entries exceeds path_cap={path_cap}")
+            if r.path_len > path_cap:  # deeper than the buffer: the reference has no limit -- run again with room
+                L.acs_greedy_destroy(h)
+                h = None
+                return greedy_search_batch(presentations, max_nodes_to_explore, cyclically_reduce_after_moves, want_visited,
+                                           device, path_cap=int(max(res[i].path_len for i in range(S))) + 4)
             if want_visited and r.status == 0:
                 vis = np.zeros((max(int(r.n_visited), 1), w), np.int8)
                 n_out = C.c_int64(0)
@@ -63,7 +66,8 @@ def greedy_search_batch(presentations, max_nodes_to_explore=10000, cyclically_re
             plist = [(int(a), int(l)) for a, l in paths[s, : r.path_len]]
             out.append((bool(r.solved), plist, info))
     finally:
-        L.acs_greedy_destroy(h)
+        if h is not None:
+            L.acs_greedy_destroy(h)
     return out
 
 

@@ -74,8 +74,15 @@ def trivialize_miller_schupp_through_search(min_n, max_n, min_w_len, max_w_len, 
             if not group:
                 continue
             if search_fn.__name__ == "greedy_search":  # all presentations of the group in one launch
-                results = [(s, p) for s, p, _ in greedy_search_batch(np.array(group, dtype=np.int8),
-                                                                     max_nodes_to_explore, False)]
+                from ..breadth_first import _raise_for
+
+                results = []
+                for s_, p_, info in greedy_search_batch(np.array(group, dtype=np.int8), max_nodes_to_explore, False):
+                    _raise_for(info["status"])  # the reference raises where a move empties a relator
+                    if not s_ and info["budget_hit"]:  # greedy.py:116-118 prints this per presentation
+                        print(f"Exiting search as number of explored nodes = {info['n_visited']} has exceeded the limit "
+                              f"{max_nodes_to_explore}")
+                    results.append((s_, p_))
             else:
                 import contextlib
                 import io

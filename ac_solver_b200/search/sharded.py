@@ -1,4 +1,8 @@
-"""Hash-partitioned breadth-first search over several GPUs of one node.
+"""Hash-partitioned breadth-first search over several GPUs of one node -- the NCCL all-to-all
+variant with a host-driven chunk loop (round 1).  The default multi-GPU search is now the native
+driver in ``search/partitioned.py`` / ``csrc/pbfs.cu`` (no host synchronisation per chunk, the
+exchange fused into the expansion kernel by peer stores); this module stays as the
+``torch.distributed`` collective baseline it is measured against, and for its gloo CPU test.
 
 One process per GPU (``torchrun``); ``torch.distributed`` (NCCL over NVLink) carries the only
 data-path collective -- an all-to-all of newly generated (state key, candidate id) records to
@@ -222,6 +226,13 @@ class GpuShardOps:
         _lib.check(self.L.acs_sbfs_scan(self.bitmap_global.data_ptr(), self.prefix_global.data_ptr(), self.nwords, s))
         return int(self.prefix_global[self.nwords].item())
 
+    def overflow_flag(self):
+        """1 if this rank's insert kernel ran out of table slots in the current chunk (it reports
+        through ctrl[1] AFTER the control block was cloned for the all-reduce), or the shard is full."""
+        t = self.torch
+        over = (self.ctrl[1] == 3).to(t.int64).reshape(1)
+        return over
+
     def find_cut(self):
         self.small[2] = -1
         a = self._recv_args(bitmap_global=self.bitmap_global.data_ptr(), prefix_global=self.prefix_global.data_ptr(),
@@ -236,9 +247,11 @@ class GpuShardOps:
         s = self._stream()
         _lib.check(self.L.acs_sbfs_rank_at(a, self.small[4:6].data_ptr(), s))
         cg, cl = (int(x) for x in self.small[4:6].cpu())
-        if self.n_local + cl > self.cap:
-            raise _lib.AcsError(f"rank {self.rank}: shard capacity {self.cap} exceeded (skewed partition); "
-                                "pass a larger cap_local")
+        full = self.torch.tensor([1 if self.n_local + cl > self.cap else 0], dtype=self.torch.int64, device=self.dev)
+        if self.world > 1 and self.torch.distributed.is_initialized():  # raise on every rank together
+            self.torch.distributed.all_reduce(full, op=self.torch.distributed.ReduceOp.MAX)
+        if int(full.item()):
+            raise _lib.AcsError(f"shard capacity {self.cap} exceeded on a rank (skewed partition); pass a larger cap_local")
         _lib.check(self.L.acs_sbfs_commit(a, s))
         self.n_local += cl
         return cg, cl
@@ -302,6 +315,9 @@ def bfs_sharded(presentation, max_nodes_to_explore=10000, cyclically_reduce_afte
         recv_c = comm.alltoall_v(send_c, counts, recv_counts)
         bitmap = comm.allreduce(ops.insert_mark(recv_keys, recv_c), "sum")
         total = ops.finish(bitmap)
+        if hasattr(ops, "overflow_flag"):  # every rank must stop together (a lone raise would hang the others)
+            if int(comm.allreduce(ops.overflow_flag(), "max").item()):
+                raise _lib.AcsError("sharded bfs: visited table overflow on one rank (skewed shard)")
         sol = None if ctrl[0] == I64_MAX else int(ctrl[0])
         err = None if ctrl[1] == I64_MAX else int(ctrl[1])
         if err is not None and (err & 3) == 3:
