@@ -56,6 +56,20 @@ class SbfsArgs(C.Structure):
     ]
 
 
+class CurriculumArgs(C.Structure):
+    """Mirror of ``acs_curriculum_args`` (include/acsolver_b200.h)."""
+
+    _fields_ = [
+        ("state", C.c_void_p), ("pool", C.c_void_p), ("pool_lens", C.c_void_p), ("lens", C.c_void_p),
+        ("action", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("truncated", C.c_void_p),
+        ("step_count", C.c_void_p), ("cur_state", C.c_void_p), ("solved", C.c_void_p), ("solved_list", C.c_void_p),
+        ("best", C.c_void_p), ("best_actions", C.c_void_p), ("action_log", C.c_void_p), ("final_obs", C.c_void_p),
+        ("final_steps", C.c_void_p), ("counters", C.c_void_p), ("err", C.c_void_p),
+        ("n", C.c_int64), ("n_states", C.c_int32), ("mrl", C.c_int32), ("horizon", C.c_int32),
+        ("log_stride", C.c_int32), ("flags", C.c_int32), ("repeat_solved_prob", C.c_float), ("seed", C.c_uint64),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 _ctx = {}
@@ -74,6 +88,9 @@ _SIGS = {
                                     C.POINTER(C.c_int64)]),
     "acs_vecenv_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int,
                                   C.c_int, C.c_int, _P]),
+    "acs_reward_transform": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double,
+                                       C.c_double, _P]),
+    "acs_vecenv_curriculum_step": (C.c_int, [_P, _P]),
     "acs_validate_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "acs_validate_batch_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int]),
     "acs_generic_batch": (C.c_int, [C.c_int, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,

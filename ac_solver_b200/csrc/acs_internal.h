@@ -61,4 +61,32 @@ cudaError_t launch_autoreset(int8_t* state, const int8_t* init, int8_t* final_ob
                              const uint8_t* trunc, int32_t* step_count, int32_t* final_steps, uint8_t* lens,
                              const uint8_t* init_lens, int64_t n, int mrl, cudaStream_t s);
 
+cudaError_t launch_reward_transform(const int32_t* reward, const uint8_t* done, double* stats, float* out, int64_t n,
+                                    double gamma, double eps, int normalize, int clip, double lo, double hi,
+                                    cudaStream_t s);
+struct CurriculumParams {
+    int8_t* state;            // [n, 2*mrl]
+    const int8_t* pool;       // [n_states, 2*mrl]
+    const uint8_t* pool_lens; // [n_states, 2]
+    uint8_t* lens;            // [n, 2]
+    const uint8_t* done;
+    const uint8_t* trunc;
+    int32_t* step_count;
+    int32_t* cur_state;       // [n]   index into the pool of each environment's episode
+    uint8_t* solved;          // [n_states]
+    int32_t* solved_list;     // [n_states] solved states in the order they were first solved
+    unsigned long long* best; // [n_states] (path length << 32 | env) of the shortest solving episode, ~0 = none
+    uint8_t* best_actions;    // [n_states, log_stride]
+    const uint8_t* action_log;  // [n, log_stride]
+    int8_t* final_obs;        // [n, 2*mrl] or null
+    int32_t* final_steps;     // [n] or null
+    long long* counters;      // [0] next unprocessed state, [1] number solved, [2] draws made, [3] episodes finished
+    int64_t n;
+    int n_states, mrl, log_stride;
+    float repeat_solved_prob;
+    unsigned long long seed;
+};
+
+cudaError_t launch_curriculum(const CurriculumParams& P, cudaStream_t s);
+
 }  // namespace acs

@@ -180,8 +180,7 @@ int acs_vecenv_step(int8_t* d_state, const int8_t* d_initial_state, const uint8_
                             !d_step_count)))
         return fail(ACS_ERR_INVALID, "null buffer");
     if (mrl < 1 || mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
-    if (d_action_log && (mrl % 4 != 0 || log_stride < 1))
-        return fail(ACS_ERR_UNSUPPORTED, "the action log needs max_relator_length % 4 == 0 and log_stride >= 1");
+    if (d_action_log && log_stride < 1) return fail(ACS_ERR_INVALID, "the action log needs log_stride >= 1");
     if (d_lens && !d_initial_lens) return fail(ACS_ERR_INVALID, "d_lens needs d_initial_lens for the auto-reset");
     acs::StepParams P{};
     P.in = d_state;
@@ -207,6 +206,72 @@ int acs_vecenv_step(int8_t* d_state, const int8_t* d_initial_state, const uint8_
     ACS_CUDA(acs::launch_step(P, s));
     ACS_CUDA(acs::launch_autoreset(d_state, d_initial_state, d_final_obs, d_done, d_truncated, d_step_count,
                                    d_final_steps, d_lens, d_initial_lens, n, mrl, s));
+    return ACS_OK;
+}
+
+int acs_reward_transform(const int32_t* d_reward, const uint8_t* d_done, double* d_stats, float* d_out, int64_t n,
+                         double gamma, double eps, int normalize, int clip, double lo, double hi, void* stream) {
+    if (n < 0 || (n > 0 && (!d_reward || !d_out || (normalize && (!d_stats || !d_done)))))
+        return fail(ACS_ERR_INVALID, "null buffer");
+    ACS_CUDA(acs::launch_reward_transform(d_reward, d_done, d_stats, d_out, n, gamma, eps, normalize, clip, lo, hi,
+                                          static_cast<cudaStream_t>(stream)));
+    return ACS_OK;
+}
+
+int acs_vecenv_curriculum_step(const acs_curriculum_args* a, void* stream) {
+    if (!a || a->n < 0) return fail(ACS_ERR_INVALID, "null argument block");
+    if (a->n > 0 && (!a->state || !a->pool || !a->pool_lens || !a->lens || !a->action || !a->reward || !a->done ||
+                     !a->truncated || !a->step_count || !a->cur_state || !a->solved || !a->solved_list || !a->best ||
+                     !a->best_actions || !a->action_log || !a->counters))
+        return fail(ACS_ERR_INVALID, "null buffer");
+    if (a->mrl < 1 || a->mrl > 64) return fail(ACS_ERR_UNSUPPORTED, "packed kernels need 1 <= mrl <= 64");
+    if (a->n_states < 1 || a->log_stride < 1) return fail(ACS_ERR_INVALID, "bad pool size / log stride");
+    acs::StepParams P{};
+    P.in = a->state;
+    P.out = a->state;
+    P.action = a->action;
+    P.lens = a->lens;
+    P.err = reinterpret_cast<unsigned long long*>(a->err);
+    P.reward = a->reward;
+    P.done = a->done;
+    P.truncated = a->truncated;
+    P.step_count = a->step_count;
+    P.n = a->n;
+    P.mrl = a->mrl;
+    P.cyclical = 1;
+    P.trusted = (a->flags & ACS_FLAG_NORMALIZED) ? 1 : 0;
+    P.lens_valid = ((a->flags & ACS_FLAG_LENS_VALID) && P.trusted) ? 1 : 0;
+    P.horizon = a->horizon;
+    P.max_reward = a->horizon * a->mrl * 2;
+    P.bulk_ok = aligned16(a->state);
+    P.action_log = a->action_log;
+    P.log_stride = a->log_stride;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ACS_CUDA(acs::launch_step(P, s));
+    acs::CurriculumParams C{};
+    C.state = a->state;
+    C.pool = a->pool;
+    C.pool_lens = a->pool_lens;
+    C.lens = a->lens;
+    C.done = a->done;
+    C.trunc = a->truncated;
+    C.step_count = a->step_count;
+    C.cur_state = a->cur_state;
+    C.solved = a->solved;
+    C.solved_list = a->solved_list;
+    C.best = reinterpret_cast<unsigned long long*>(a->best);
+    C.best_actions = a->best_actions;
+    C.action_log = a->action_log;
+    C.final_obs = a->final_obs;
+    C.final_steps = a->final_steps;
+    C.counters = reinterpret_cast<long long*>(a->counters);
+    C.n = a->n;
+    C.n_states = a->n_states;
+    C.mrl = a->mrl;
+    C.log_stride = a->log_stride;
+    C.repeat_solved_prob = a->repeat_solved_prob;
+    C.seed = a->seed;
+    ACS_CUDA(acs::launch_curriculum(C, s));
     return ACS_OK;
 }
 

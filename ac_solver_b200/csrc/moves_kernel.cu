@@ -106,6 +106,8 @@ __device__ __forceinline__ void write_row_outputs(const StepParams& P, int64_t r
         int sc = P.step_count[row] + 1;
         P.step_count[row] = sc;
         P.truncated[row] = (uint8_t)(sc >= P.horizon);
+        if (P.action_log)  // ACEnv.actions (ac_env.py:96)
+            P.action_log[row * P.log_stride + min(sc - 1, P.log_stride - 1)] = P.action[row];
     }
 }
 
@@ -503,6 +505,165 @@ cudaError_t launch_autoreset(int8_t* state, const int8_t* init, int8_t* final_ob
         reinterpret_cast<uint16_t*>(state), reinterpret_cast<const uint16_t*>(init),
         reinterpret_cast<uint16_t*>(final_obs), done, trunc, step_count, final_steps, reinterpret_cast<uint16_t*>(lens),
         reinterpret_cast<const uint16_t*>(init_lens), n, mrl);
+    return cudaGetLastError();
+}
+
+
+// ---- reward wrappers of the PPO environment, per environment and on the device ------------------
+// gymnasium 0.28.1 NormalizeReward (agents/environment.py:45-46; one wrapper per environment):
+//   returns = returns * gamma * (1 - terminated) + reward;  rms.update([returns]);
+//   reward  = reward / sqrt(rms.var + eps)          (RunningMeanStd: mean 0, var 1, count 1e-4)
+// followed by TransformReward(clip) (environment.py:48-52).  stats = [4][n] doubles: returns,
+// mean, var, count.  (Recalled semantics: the gymnasium package is not available here, so this
+// wrapper is "parity unpinned" like the rest of the vector-env shell.)
+__global__ void __launch_bounds__(256) env_reward_transform_kernel(const int32_t* reward, const uint8_t* done,
+                                                                   double* stats, float* out, int64_t n, double gamma,
+                                                                   double eps, int normalize, int clip, double lo,
+                                                                   double hi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = (double)reward[i];
+    if (normalize) {
+        double ret = stats[i] * gamma * (done[i] ? 0.0 : 1.0) + r;
+        double mean = stats[n + i], var = stats[2 * n + i], count = stats[3 * n + i];
+        const double delta = ret - mean, tot = count + 1.0;  // batch of one: batch_var = 0
+        const double new_mean = mean + delta / tot;
+        const double m2 = var * count + delta * delta * count / tot;
+        stats[i] = ret;
+        stats[n + i] = new_mean;
+        stats[2 * n + i] = m2 / tot;
+        stats[3 * n + i] = tot;
+        r = r / sqrt(m2 / tot + eps);
+    }
+    if (clip) r = fmin(fmax(r, lo), hi);
+    out[i] = (float)r;
+}
+
+cudaError_t launch_reward_transform(const int32_t* reward, const uint8_t* done, double* stats, float* out, int64_t n,
+                                    double gamma, double eps, int normalize, int clip, double lo, double hi,
+                                    cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    env_reward_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reward, done, stats, out, n, gamma, eps,
+                                                                            normalize, clip, lo, hi);
+    return cudaGetLastError();
+}
+
+// ---- curriculum reset of the PPO rollout, on the device (agents/training.py:169-224) -----------
+// Finished environments (done | truncated) record their result and move on to another initial state
+// of the pool: round one hands out the not yet processed states in order (in environment order, as
+// the reference's sequential loop does); afterwards an unsolved state with probability
+// 1 - repeat_solved_prob (or when nothing is solved yet), else a solved one, uniformly.  The
+// reference draws from Python's `random`; here a counter-based hash of (seed, draw index)
+// supplies the uniform numbers (same distribution, not the same stream), and the solved set seen by
+// a draw is the one at the END of the step.  ONE block (the environment count is in the thousands).
+__device__ __forceinline__ unsigned long long cur_mix(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__global__ void __launch_bounds__(1024) env_curriculum_kernel(const CurriculumParams P) {
+    __shared__ unsigned s_warp[32];
+    __shared__ long long s_base, s_draw0;
+    __shared__ int s_nsolved;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rowb = 2 * P.mrl;
+    if (tid == 0) {
+        s_base = P.counters[0];
+        s_draw0 = P.counters[2];
+    }
+    __syncthreads();
+    // ---- pass 1: results of the finished episodes (training.py:170-189) ----
+    for (int64_t i = tid; i < P.n; i += blockDim.x) {
+        if (!(P.done[i] | P.trunc[i])) continue;
+        if (P.final_steps) P.final_steps[i] = P.step_count[i];
+        if (P.done[i]) {
+            const int st = P.cur_state[i];
+            // `solved` is a byte per state; the first solver appends the state to the solved list
+            unsigned int* word = reinterpret_cast<unsigned int*>(P.solved + (st & ~3));
+            const unsigned int bit = 1u << (8 * (st & 3));
+            if (!(atomicOr(word, bit) & bit)) P.solved_list[atomicAdd((unsigned long long*)&P.counters[1], 1ull)] = st;
+            atomicMin(&P.best[st], ((unsigned long long)P.step_count[i] << 32) | (unsigned long long)i);
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    for (int64_t i = tid; i < P.n; i += blockDim.x) {  // the shortest solving episode keeps its action sequence
+        if (!P.done[i]) continue;
+        const int st = P.cur_state[i];
+        if (P.best[st] == (((unsigned long long)P.step_count[i] << 32) | (unsigned long long)i)) {
+            const int len = min(P.step_count[i], P.log_stride);
+            for (int k = 0; k < len; ++k) P.best_actions[(int64_t)st * P.log_stride + k] = P.action_log[i * P.log_stride + k];
+        }
+    }
+    if (tid == 0) s_nsolved = (int)P.counters[1];
+    __syncthreads();
+    // ---- pass 2: the next initial state of every finished environment, in environment order ----
+    long long fin_seen = 0;
+    for (int64_t i0 = 0; i0 < P.n; i0 += blockDim.x) {
+        const int64_t i = i0 + tid;
+        const bool fin = i < P.n && (P.done[i] | P.trunc[i]);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, fin);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        long long before = fin_seen + __popc(bal & ((1u << lane) - 1u));
+        long long chunk_total = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            if (w < wid) before += s_warp[w];
+            chunk_total += s_warp[w];
+        }
+        if (fin) {
+            const long long cand = s_base + before;  // round one: max(states_processed) + 1 (training.py:206-207)
+            int next;
+            if (cand < P.n_states) {
+                next = (int)cand;
+            } else {
+                const unsigned long long d = (unsigned long long)(s_draw0 + before) * 8;
+                const float u = (float)(cur_mix(P.seed ^ cur_mix(d)) >> 40) * (1.0f / 16777216.0f);
+                const int ns = s_nsolved, nu = P.n_states - ns;
+                if (ns == 0 || (nu > 0 && u > P.repeat_solved_prob)) {  // training.py:210-217
+                    next = -1;
+                    for (int t = 1; t <= 6 && next < 0; ++t) {  // rejection sampling of an unsolved state
+                        const int c = (int)(cur_mix(P.seed ^ cur_mix(d + t)) % (unsigned long long)P.n_states);
+                        if (!P.solved[c]) next = c;
+                    }
+                    if (next < 0) {  // dense solved set: first unsolved state after a random start
+                        int c = (int)(cur_mix(P.seed ^ cur_mix(d + 7)) % (unsigned long long)P.n_states);
+                        for (int t = 0; t < P.n_states && P.solved[c]; ++t) c = c + 1 == P.n_states ? 0 : c + 1;
+                        next = c;
+                    }
+                } else {
+                    next = P.solved_list[cur_mix(P.seed ^ cur_mix(d + 1)) % (unsigned long long)ns];
+                }
+            }
+            P.cur_state[i] = next;
+            int8_t* row = P.state + i * rowb;
+            const int8_t* src = P.pool + (int64_t)next * rowb;
+            for (int k = 0; k < rowb; ++k) {
+                if (P.final_obs) P.final_obs[i * rowb + k] = row[k];
+                row[k] = src[k];
+            }
+            P.lens[2 * i] = P.pool_lens[2 * next];
+            P.lens[2 * i + 1] = P.pool_lens[2 * next + 1];
+            P.step_count[i] = 0;
+        }
+        fin_seen += chunk_total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const long long used = min((long long)P.n_states - s_base, fin_seen);
+        P.counters[0] = s_base + (used > 0 ? used : 0);
+        P.counters[2] = s_draw0 + fin_seen;
+        P.counters[3] += fin_seen;
+    }
+}
+
+cudaError_t launch_curriculum(const CurriculumParams& P, cudaStream_t s) {
+    if (P.n <= 0) return cudaSuccess;
+    env_curriculum_kernel<<<1, 1024, 0, s>>>(P);
     return cudaGetLastError();
 }
 

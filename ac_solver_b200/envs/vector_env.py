@@ -70,10 +70,12 @@ class _EnvProxy:
 
 
 class ACVectorEnv:
-    def __init__(self, initial_states, horizon_length=1000, device=None, clip_rewards=None, use_supermoves=False):
+    def __init__(self, initial_states, horizon_length=1000, device=None, clip_rewards=None, use_supermoves=False,
+                 norm_rewards=False, gamma=0.99):
         """initial_states: [N, 2*mrl] presentations (one per environment), all valid
         (``ACEnvConfig.__post_init__``, ac_env.py:22-35).  clip_rewards: optional (min, max) as in
-        ``TransformReward(np.clip)`` (environment.py:48-52)."""
+        ``TransformReward(np.clip)`` (environment.py:48-52).  norm_rewards / gamma: gymnasium's
+        ``NormalizeReward`` per environment (environment.py:45-46), applied before the clip."""
         import torch
 
         if use_supermoves:
@@ -117,7 +119,15 @@ class ACVectorEnv:
         # general kernel variant; states produced by the kernel are normal forms, and so are most
         # datasets (ACS_FLAG_NORMALIZED | ACS_FLAG_LENS_VALID is the steady state).
         self._normalized = bool(self.initial_normal_host.all())
-        self._fast_ok = self._normalized and self.max_relator_length % 4 == 0
+        # the sync-free path runs ONE kernel variant per environment object: the steady-state variant when
+        # every initial state is a normal form, else the general one (full simplification of both relators)
+        self._device_flags = (_lib.FLAG_NORMALIZED | _lib.FLAG_LENS_VALID) if self._normalized else 0
+        self.norm_rewards, self.gamma = bool(norm_rewards), float(gamma)
+        self.reward_stats = torch.zeros((4, n), dtype=torch.float64, device=self.dev)  # returns, mean, var, count
+        self.reward_stats[2] = 1.0
+        self.reward_stats[3] = 1e-4
+        self.reward_out = torch.zeros(n, dtype=torch.float32, device=self.dev)
+        self._curriculum = None
         self.final_obs = torch.zeros_like(self.state)
         self.final_steps = torch.zeros(n, dtype=torch.int32, device=self.dev)
         self.envs = [_EnvProxy(self, i) for i in range(n)]
@@ -135,10 +145,10 @@ class ACVectorEnv:
         self.step_count[idx] = 0
         # normal forms keep the steady-state kernel variant valid; anything else forces one
         # general step (which re-simplifies and recounts every row)
-        if _normal_form_mask(s).all():
-            self.lens[idx] = t.from_numpy(_lens_of(s)).to(self.dev)
-        else:
+        self.lens[idx] = t.from_numpy(_lens_of(s)).to(self.dev)
+        if not _normal_form_mask(s).all():
             self._normalized = False
+            self._device_flags = 0  # from now on the sync-free path runs the general kernel variant
 
     def reset(self, *, seed=None, options=None):
         """All environments back to their initial states -> (obs, {})."""
@@ -172,9 +182,12 @@ class ACVectorEnv:
         if n_bad:
             raise AssertionError(f"{n_bad} environments produced an invalid presentation (first: env {int(self.err[1])}); "
                                  "the reference raises AssertionError here (envs/utils.py:261-263)")
-        reward = self.reward.to(t.float64)
-        if self.clip_rewards is not None:
-            reward = reward.clamp(self.clip_rewards[0], self.clip_rewards[1])
+        if self.norm_rewards:
+            reward = self.transformed_reward().to(t.float64)
+        else:
+            reward = self.reward.to(t.float64)
+            if self.clip_rewards is not None:
+                reward = reward.clamp(self.clip_rewards[0], self.clip_rewards[1])
         infos = {}
         obs = self.state
         if any_fin:
@@ -213,21 +226,100 @@ class ACVectorEnv:
         Finished environments are already reset in ``obs``; their last observation is in
         ``self.final_obs``, the episode length in ``self.final_steps`` and -- for solved ones --
         the move sequence via ``final_actions(i)``.  Reward clipping (if configured) is applied by
-        ``clipped_reward()``.  Errors (a move emptying a relator) accumulate in ``self.err`` and
-        are raised by ``check_errors()``."""
+        ``clipped_reward()`` / ``transformed_reward()``.  Errors (a move emptying a relator) accumulate in
+        ``self.err`` and are raised by ``check_errors()``; the outputs of such a row are zero for that step.
+        With ``enable_curriculum`` finished environments continue with another state of the pool instead of
+        their own initial state.  Any max_relator_length <= 64 and non-normal-form initial states are served
+        (by the general kernel variant)."""
         t = self.torch
-        if not (self._fast_ok and self._normalized):
-            raise _lib.AcsError("step_device needs normal-form states (initial and planted) and "
-                                "max_relator_length % 4 == 0; use step()")
         act = actions if actions.dtype == t.uint8 else actions.to(t.uint8)
+        stream = t.cuda.current_stream(self.dev).cuda_stream
+        if self._curriculum is not None:
+            a = self._curriculum["args"]
+            a.action = act.data_ptr()
+            a.flags = self._device_flags
+            _lib.check(self.L.acs_vecenv_curriculum_step(__import__("ctypes").byref(a), stream))
+            return self.state, self.reward, self.done, self.truncated
         _lib.check(self.L.acs_vecenv_step(
             self.state.data_ptr(), self.initial_states.data_ptr(), act.data_ptr(), self.reward.data_ptr(),
             self.done.data_ptr(), self.truncated.data_ptr(), self.step_count.data_ptr(), self.lens.data_ptr(),
             self.initial_lens.data_ptr(), self.action_log.data_ptr(), self.action_log.shape[1],
             self.final_obs.data_ptr(), self.final_steps.data_ptr(), self.err.data_ptr(), self.num_envs,
-            self.max_relator_length, self.horizon_length, _lib.FLAG_NORMALIZED | _lib.FLAG_LENS_VALID,
-            t.cuda.current_stream(self.dev).cuda_stream))
+            self.max_relator_length, self.horizon_length, self._device_flags, stream))
         return self.state, self.reward, self.done, self.truncated
+
+    def transformed_reward(self):
+        """Rewards of the last step as the PPO loop receives them: ``NormalizeReward`` (if configured, per
+        environment, running statistics kept on the device) then the clip.  float32 CUDA tensor; sync-free."""
+        t = self.torch
+        clip = self.clip_rewards is not None
+        lo, hi = (self.clip_rewards if clip else (0.0, 0.0))
+        _lib.check(self.L.acs_reward_transform(
+            self.reward.data_ptr(), self.done.data_ptr(), self.reward_stats.data_ptr(), self.reward_out.data_ptr(),
+            self.num_envs, self.gamma, 1e-8, int(self.norm_rewards), int(clip), float(lo), float(hi),
+            t.cuda.current_stream(self.dev).cuda_stream))
+        return self.reward_out
+
+    # ---- device-side curriculum (training.py:169-224) ------------------------------------------
+    def enable_curriculum(self, pool_states, repeat_solved_prob=0.25, seed=0):
+        """Let ``step_device`` move finished environments on to other initial states of ``pool_states``
+        ([n_states, 2*mrl]; the first num_envs rows are the environments' current initial states) exactly
+        as the reference's rollout loop does on the host, without leaving the device."""
+        import ctypes as C
+
+        t = self.torch
+        pool = np.ascontiguousarray(pool_states, dtype=np.int8)
+        if pool.ndim != 2 or pool.shape[1] != 2 * self.max_relator_length or len(pool) < self.num_envs:
+            raise ValueError("pool_states must be [n_states >= num_envs, 2*max_relator_length]")
+        for row in pool:
+            assert is_array_valid_presentation(row), f"{row} is not a valid presentation"
+        if not np.array_equal(pool[: self.num_envs], self.initial_states_host):
+            raise ValueError("the first num_envs pool states must be the environments' initial states")
+        if not _normal_form_mask(pool).all():
+            self._device_flags = 0
+        ns = len(pool)
+        c = {
+            "pool": t.from_numpy(pool).to(self.dev), "pool_lens": t.from_numpy(_lens_of(pool)).to(self.dev),
+            "cur_state": t.arange(self.num_envs, dtype=t.int32, device=self.dev),
+            "solved": t.zeros((ns + 3) // 4 * 4, dtype=t.uint8, device=self.dev),
+            "solved_list": t.zeros(ns, dtype=t.int32, device=self.dev),
+            "best": t.full((ns,), -1, dtype=t.int64, device=self.dev),
+            "best_actions": t.zeros((ns, self.action_log.shape[1]), dtype=t.uint8, device=self.dev),
+            "counters": t.tensor([self.num_envs, 0, 0, 0], dtype=t.int64, device=self.dev), "n_states": ns,
+        }
+        a = _lib.CurriculumArgs()
+        a.state, a.pool, a.pool_lens, a.lens = (self.state.data_ptr(), c["pool"].data_ptr(), c["pool_lens"].data_ptr(),
+                                                self.lens.data_ptr())
+        a.reward, a.done, a.truncated, a.step_count = (self.reward.data_ptr(), self.done.data_ptr(),
+                                                       self.truncated.data_ptr(), self.step_count.data_ptr())
+        a.cur_state, a.solved, a.solved_list, a.best = (c["cur_state"].data_ptr(), c["solved"].data_ptr(),
+                                                        c["solved_list"].data_ptr(), c["best"].data_ptr())
+        a.best_actions, a.action_log = c["best_actions"].data_ptr(), self.action_log.data_ptr()
+        a.final_obs, a.final_steps = self.final_obs.data_ptr(), self.final_steps.data_ptr()
+        a.counters, a.err = c["counters"].data_ptr(), self.err.data_ptr()
+        a.n, a.n_states, a.mrl, a.horizon = self.num_envs, ns, self.max_relator_length, self.horizon_length
+        a.log_stride, a.flags = self.action_log.shape[1], self._device_flags
+        a.repeat_solved_prob, a.seed = float(repeat_solved_prob), int(seed) & (2 ** 64 - 1)
+        c["args"] = a
+        self._curriculum = c
+        del C
+
+    def success_record(self):
+        """``success_record`` of the reference's loop: {"solved": set, "unsolved": set} of pool indices."""
+        c = self._curriculum
+        solved = set(int(i) for i in np.flatnonzero(c["solved"][: c["n_states"]].cpu().numpy()))
+        return {"solved": solved, "unsolved": set(range(c["n_states"])) - solved}
+
+    def acmoves_hist(self):
+        """``ACMoves_hist``: the shortest action sequence that solved each pool state so far."""
+        c = self._curriculum
+        best = c["best"].cpu().numpy()
+        acts = c["best_actions"].cpu().numpy()
+        return {int(s): [int(x) for x in acts[s, : int(best[s] >> 32)]] for s in np.flatnonzero(best >= 0)}
+
+    def curriculum_counters(self):
+        nxt, n_solved, draws, episodes = (int(v) for v in self._curriculum["counters"].cpu())
+        return {"next_unprocessed": nxt, "n_solved": n_solved, "random_draws": draws, "episodes": episodes}
 
     def clipped_reward(self):
         r = self.reward.to(self.torch.float32)

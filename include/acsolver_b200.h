@@ -116,6 +116,44 @@ int acs_vecenv_step(int8_t *d_state, const int8_t *d_initial_state, const uint8_
                     int32_t *d_final_steps, uint64_t *d_err, int64_t n, int mrl, int horizon, int flags,
                     void *stream);
 
+/* ---- reward wrappers and curriculum of the PPO rollout, on the device ---------------------------- */
+/* gymnasium 0.28.1 NormalizeReward per environment (agents/environment.py:45-46) followed by the
+ * TransformReward clip (environment.py:48-52).  d_stats: [4][n] doubles (returns, mean, var, count;
+ * initialise to 0, 0, 1, 1e-4).  d_out: float rewards as PPO consumes them. */
+int acs_reward_transform(const int32_t *d_reward, const uint8_t *d_done, double *d_stats, float *d_out, int64_t n,
+                         double gamma, double eps, int normalize, int clip, double lo, double hi, void *stream);
+/* One vector-env step with the reference's curriculum reset (agents/training.py:169-224) on the
+ * device: finished environments record their result (solved set, shortest action sequence per
+ * initial state -- success_record / ACMoves_hist) and continue with another initial state of the
+ * pool: the unprocessed ones in order first, then an unsolved one with probability
+ * 1 - repeat_solved_prob (or while nothing is solved), else a solved one.  No host involvement;
+ * capturable in a CUDA graph.  counters: {next unprocessed state, number solved, draws, episodes}. */
+typedef struct {
+    int8_t *state;             /* [n, 2*mrl] */
+    const int8_t *pool;        /* [n_states, 2*mrl] initial states */
+    const uint8_t *pool_lens;  /* [n_states, 2] */
+    uint8_t *lens;             /* [n, 2] */
+    const uint8_t *action;     /* [n] */
+    int32_t *reward;
+    uint8_t *done, *truncated;
+    int32_t *step_count;
+    int32_t *cur_state;        /* [n] pool index of each environment's current episode */
+    uint8_t *solved;           /* [n_states rounded up to 4] */
+    int32_t *solved_list;      /* [n_states] */
+    uint64_t *best;            /* [n_states] (length << 32 | env) of the shortest solving episode, ~0 = none */
+    uint8_t *best_actions;     /* [n_states, log_stride] */
+    uint8_t *action_log;       /* [n, log_stride] */
+    int8_t *final_obs;         /* [n, 2*mrl] or NULL */
+    int32_t *final_steps;      /* [n] or NULL */
+    int64_t *counters;         /* [4] */
+    uint64_t *err;             /* {count, min row} or NULL */
+    int64_t n;
+    int32_t n_states, mrl, horizon, log_stride, flags;
+    float repeat_solved_prob;
+    uint64_t seed;
+} acs_curriculum_args;
+int acs_vecenv_curriculum_step(const acs_curriculum_args *a, void *stream);
+
 /* ---- boundary validation (envs/utils.py:13-54) ------------------------------------ */
 /* flags[row]: bit0 is_array_valid_presentation, bit1 letters in {0,+-1,+-2},
  * bit2 zeros only on the right of each half. */
