@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--bfs-timeout", type=float, default=240.0)
     ap.add_argument("--skip-python-baseline", action="store_true")
     ap.add_argument("--skip-greedy", action="store_true")
+    ap.add_argument("--skip-vecenv", action="store_true")
     ap.add_argument("--greedy-budget", type=int, default=1_000_000)
     return ap.parse_args()
 
@@ -488,6 +489,11 @@ def run_b200(args):
     dog = threading.Timer(args.bfs_timeout, bail)
     dog.daemon = True
     dog.start()
+    if world == 1 and not args.skip_vecenv:
+        try:
+            line["vecenv"] = bench_vecenv(args)
+        except Exception as e:
+            line["vecenv"] = {"error": repr(e)}
     if not args.skip_greedy:
         try:
             greedy_line = bench_greedy(args, world, dist)
@@ -699,6 +705,101 @@ def bench_greedy(args, world=1, dist=None):
                                "sample": f"C oracle greedy_search on {len(sample)} of the {len(unsolved)} unsolved rows at budget "
                                          f"{budget}, one search per thread on {cores} threads: {cs:.1f} s; the 533 solved rows are cheap",
                                "speedup_vs_allcore_port_wall": est / wall, "speedup_vs_allcore_port_device": est / dev_s}
+    return out
+
+
+def bench_vecenv(args):
+    """BASELINE.json configs[3]: PPO rollout, environment side -- 4096 GPU-resident environments, horizon
+    200, the reference's 2x512 tanh actor (agents/ppo_agent.py:39-49) sampling actions on the device, reward
+    NormalizeReward + clip and the curriculum reset of training.py:169-224 all on the device; policy forward,
+    sampling, env step, reset and reward transform are ONE CUDA graph.  Reported: environment steps / s.
+    CPU beside it: the C oracle stepping the same 4096 rows, and the reference's own ACEnv.step loop."""
+    import torch
+    from ast import literal_eval
+
+    from ac_solver_b200.envs.vector_env import ACVectorEnv
+
+    n_envs, horizon, replays = 4096, 200, 1000
+    data = os.path.join(ROOT, "ac_solver_b200", "search", "miller_schupp", "data", "all_presentations.txt")
+    with open(data) as f:
+        rows = [np.array(literal_eval(line), dtype=np.int8) for line in f if line.strip()]
+    pad = np.zeros((len(rows), 72), np.int8)
+    for k, r in enumerate(rows):  # change_max_relator_length_of_presentation(., 36) (environment.py:88-93)
+        m = r.size // 2
+        pad[k, :m], pad[k, 36 : 36 + m] = r[:m], r[m:]
+    pool = pad[np.arange(2 * n_envs) % len(pad)]
+    env = ACVectorEnv(pool[:n_envs], horizon_length=horizon, clip_rewards=(-10, 1000), norm_rewards=True, gamma=0.99)
+    env.reset()
+    env.enable_curriculum(pool, repeat_solved_prob=0.25, seed=0)
+    torch.manual_seed(0)
+    actor = torch.nn.Sequential(torch.nn.Linear(72, 512), torch.nn.Tanh(), torch.nn.Linear(512, 512), torch.nn.Tanh(),
+                                torch.nn.Linear(512, 12)).cuda()
+
+    def rollout_step():
+        with torch.no_grad():
+            logits = actor(env.state.float())
+            g = -torch.log(-torch.log(torch.rand_like(logits).clamp_(1e-10, 1.0)))  # Gumbel-max == Categorical sampling
+            env.step_device((logits + g).argmax(dim=1))
+            return env.transformed_reward()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            rollout_step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        rollout_step()
+    for _ in range(20):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(replays):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    env.check_errors()
+    c = env.curriculum_counters()
+    out = {
+        "metric": "PPO rollout env steps/sec (env side)", "workload": "BASELINE.json configs[3]: 4096 envs, horizon 200, "
+        "torch 2x512 actor on device, device-side NormalizeReward+clip and curriculum reset, one CUDA graph per vector step",
+        "env_steps_per_s": n_envs * replays / (ms * 1e-3), "us_per_vector_step": 1e3 * ms / replays,
+        "episodes_finished": c["episodes"], "states_solved": c["n_solved"], "host_syncs_per_step": 0,
+    }
+    from oracle import oracle as O
+
+    S, sc = pool[:n_envs].copy(), np.zeros(n_envs, np.int32)
+    A = np.random.default_rng(0).integers(0, 12, size=n_envs).astype(np.uint8)
+    for threads in (1, host_threads()):
+        O.env_step_batch(S, A, sc, horizon, nthreads=threads)
+        t0, reps = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 1.0:
+            O.env_step_batch(S, A, sc, horizon, nthreads=threads)
+            reps += 1
+        out[f"cpu_port_env_steps_per_s_{threads}_threads"] = n_envs * reps / (time.perf_counter() - t0)
+    try:  # the reference's own ACEnv.step loop (pure Python), 64 environments x 200 steps, one core
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        from ac_solver.envs.ac_env import ACEnv, ACEnvConfig
+
+        envs = [ACEnv(ACEnvConfig(initial_state=pool[k].copy(), horizon_length=horizon)) for k in range(64)]
+        rng = np.random.default_rng(1)
+        t0, steps = time.perf_counter(), 0
+        for _ in range(200):
+            for e in envs:
+                try:
+                    _, _, d, tr, _ = e.step(int(rng.integers(0, 12)))
+                except AssertionError:
+                    d = True
+                if d or tr:
+                    e.reset()
+                steps += 1
+        out["cpu_baseline_python"] = {"value": steps / (time.perf_counter() - t0), "unit": "env steps/s", "cores": 1,
+                                      "kind": "reference", "sample": "the reference's ACEnv.step, 64 envs x 200 steps, one core"}
+    except Exception as e:
+        out["cpu_baseline_python"] = {"unavailable": repr(e)}
     return out
 
 
