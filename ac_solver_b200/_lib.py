@@ -116,6 +116,8 @@ _SIGS = {
     "acs_sbfs_lower_bound": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     "acs_sbfs_lookup": (C.c_int, [_P, C.c_int64, _P, _P]),
     "acs_sbfs_unpack": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
+    "acs_ball_explore": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), _P,
+                                   _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "acs_pbfs_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.POINTER(_P)]),
     "acs_pbfs_export": (C.c_int, [_P, _P]),
     "acs_pbfs_connect": (C.c_int, [_P, C.c_char_p]),

@@ -287,6 +287,18 @@ int acs_pbfs_stats(acs_pbfs *b, int64_t *out8);
 int acs_pbfs_set_timeout(acs_pbfs *b, double seconds);
 void acs_pbfs_destroy(acs_pbfs *b);
 
+/* ---- barcode_analysis state model: unordered relator pairs, full free reduction ----
+ * Replaces the BFS of barcode_analysis/5_steps_neibourhoods/neibourhoods.cpp:18-54 (size of the
+ * radius-r ball: radius >= 0, size_cap 0) and of barcode_analysis/simplex_data_generation/<prime|classic>_moves/
+ * ac_bfs.cpp:36-91 (all states of total length <= size_cap, radius < 0, with the 0/1-simplices and
+ * their filtration values).  h_letters: relator 1 then relator 2 as letters +-1, +-2 (no padding).
+ * classic != 0: the 14 classic moves, else the 12 prime moves (AC_UTILS_no_hash.cpp:153-211).
+ * Nodes are numbered in the reference's FIFO discovery order.  h_sizes / h_levels (capacity cap_nodes),
+ * h_edges ((cn, cc, filtration) uint32 triples, capacity cap_edges) may be NULL. */
+int acs_ball_explore(int device, const int8_t *h_letters, int len1, int len2, int radius, int size_cap, int classic,
+                     int64_t max_nodes, int64_t *n_nodes_out, uint16_t *h_sizes, uint8_t *h_levels, int64_t cap_nodes,
+                     uint32_t *h_edges, int64_t cap_edges, int64_t *n_edges_out);
+
 #ifdef __cplusplus
 }
 #endif
