@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libacsolver_b200.so")
 
 ACS_OK = 0
+ACS_ERR_INVALID, ACS_ERR_CUDA, ACS_ERR_UNSUPPORTED, ACS_ERR_NOMEM, ACS_ERR_NO_DEVICE = -1, -2, -3, -4, -5
 ROW_OK, ROW_ASSERT, ROW_INDEX = 0, 1, 2
 OP_ACMOVE, OP_CONCAT_RAW, OP_CONJ_RAW, OP_SIMPLIFY_RELATOR, OP_SIMPLIFY_PRESENTATION = range(5)
 FLAG_CYCLICAL, FLAG_NORMALIZED, FLAG_LENS_VALID = 1, 2, 4
@@ -118,6 +119,11 @@ _SIGS = {
     "acs_sbfs_unpack": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "acs_ball_explore": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int64), _P,
                                    _P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "acs_gae": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int64, C.c_double, C.c_double, _P]),
+    "acs_ppo_loss_workspace_bytes": (C.c_int, []),
+    "acs_ppo_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_double, C.c_double, C.c_double, _P]),
+    "acs_ball_sizes": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "acs_pbfs_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.POINTER(_P)]),
     "acs_pbfs_export": (C.c_int, [_P, _P]),
     "acs_pbfs_connect": (C.c_int, [_P, C.c_char_p]),

@@ -61,9 +61,46 @@ def neighbourhood_size(presentation, radius=5, classic=False, max_nodes=4_000_00
     return _explore(r1, r2, radius, 0, classic, max_nodes, device=device)["n_nodes"]
 
 
-def neighbourhood_sizes(presentations, radius=5, classic=False, **kw):
-    """neibourhoods.cpp ``read_do_and_write`` for a list of presentations."""
-    return [neighbourhood_size(p, radius, classic, **kw) for p in presentations]
+def _ball_batch(rels, radius, classic, max_nodes, device):
+    L = _lib.lib()
+    letters = np.ascontiguousarray(np.concatenate([np.concatenate(r) for r in rels] + [np.zeros(1, np.int8)]), dtype=np.int8)
+    off = np.zeros(2 * len(rels) + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for r in rels for x in r])
+    counts = np.zeros(len(rels), np.int64)
+    rc = L.acs_ball_sizes(device, letters.ctypes.data, off.ctypes.data, len(rels), int(radius), int(bool(classic)),
+                          int(max_nodes), counts.ctypes.data)
+    return rc, counts
+
+
+def neighbourhood_sizes(presentations, radius=5, classic=False, batch_roots=128, batch_bytes=12 << 30, device=None):
+    """neibourhoods.cpp ``read_do_and_write`` (:58-103) for a list of presentations: the balls of a batch of
+    presentations are explored TOGETHER (one breadth-first run over (root, state) pairs, csrc/ball.cu), batches
+    sized so that the node store stays below ``batch_bytes``; a batch that outgrows its store is split."""
+    rels = [_relators(p) for p in presentations]
+    dev = _lib.default_device() if device is None else device
+    out = np.zeros(len(rels), np.int64)
+
+    def stride(batch):  # the engine's letter stride for this batch (ball.cu: a relator at most doubles per move)
+        a = b = max(1, max(max(len(r[0]), len(r[1])) for r in batch))
+        for _ in range(max(radius, 0)):
+            a, b = max(a + b, max(a, b) + 2), max(a, b)
+        return (min(max(max(a, b) + 2, 4), 512) + 3) // 4 * 4
+
+    def run(lo, hi):
+        batch = rels[lo:hi]
+        max_nodes = max(int(batch_bytes // (2 * stride(batch) + 16)), len(batch) + 1024)
+        rc, counts = _ball_batch(batch, radius, classic, max_nodes, dev)
+        if rc == _lib.ACS_ERR_NOMEM and hi - lo > 1:  # more states than the store holds: halve the batch
+            mid = (lo + hi) // 2
+            run(lo, mid)
+            run(mid, hi)
+            return
+        _lib.check(rc)
+        out[lo:hi] = counts
+
+    for lo in range(0, len(rels), batch_roots):
+        run(lo, min(lo + batch_roots, len(rels)))
+    return [int(x) for x in out]
 
 
 def simplex_data(n, classic=False, max_nodes=50_000_000, device=None):

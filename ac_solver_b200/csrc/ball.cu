@@ -35,6 +35,7 @@ struct BallArgs {
     int8_t* nodes;      // [cap][stride]  rel1 letters [0,L), rel2 letters [L,2L)
     uint16_t* lens;     // [cap][2]
     uint8_t* level;     // [cap]
+    uint32_t* root_of;  // [cap]  index of the start presentation this node was reached from (multi-root runs)
     uint64_t* table;    // [tmask+1]  fp24 << 40 | index+1 ; index >= n_nodes: tentative candidate n_nodes + c
     uint64_t tmask;
     int8_t* cand;       // [ccap][stride]
@@ -56,8 +57,8 @@ __device__ __forceinline__ bool rel_less(const int8_t* x, int lx, const int8_t* 
         if (x[i] != y[i]) return x[i] < y[i];
     return false;
 }
-__device__ __forceinline__ uint64_t ball_hash(const int8_t* r1, int l1, const int8_t* r2, int l2) {
-    uint64_t h = 0xcbf29ce484222325ull ^ ((uint64_t)l1 << 32 | (uint64_t)l2);
+__host__ __device__ __forceinline__ uint64_t ball_hash(const int8_t* r1, int l1, const int8_t* r2, int l2, uint32_t root) {
+    uint64_t h = (0xcbf29ce484222325ull ^ ((uint64_t)l1 << 32 | (uint64_t)l2)) + 0x9E3779B97F4A7C15ull * root;
     for (int i = 0; i < l1; ++i) h = (h ^ (uint8_t)r1[i]) * 0x100000001b3ull;
     h = (h ^ 0xFF) * 0x100000001b3ull;
     for (int i = 0; i < l2; ++i) h = (h ^ (uint8_t)r2[i]) * 0x100000001b3ull;
@@ -191,7 +192,8 @@ __global__ void __launch_bounds__(kBallThreads) ball_insert_kernel(const BallArg
     uint32_t my_slot = 0xFFFFFFFFu;
     if (cl[0] != 0xFFFF) {
         const int8_t* me = A.cand + c * 2 * L;
-        const uint64_t h = ball_hash(me, cl[0], me + L, cl[1]);
+        const uint32_t my_root = A.root_of[A.lo + c / A.K];
+        const uint64_t h = ball_hash(me, cl[0], me + L, cl[1], my_root);
         const uint64_t fp = h >> 40;
         const uint64_t mine = (fp << 40) | (A.n_nodes + c + 1);
         for (uint64_t s = h & A.tmask;; s = (s + 1) & A.tmask) {
@@ -206,8 +208,9 @@ __global__ void __launch_bounds__(kBallThreads) ball_insert_kernel(const BallArg
             if ((cur >> 40) == fp) {
                 const uint64_t idx = (cur & kBallIdxMask) - 1;
                 const bool same = idx < A.n_nodes
-                                      ? ball_same(me, cl, A.nodes + idx * 2 * L, A.lens + 2 * idx, L)
-                                      : ball_same(me, cl, A.cand + (idx - A.n_nodes) * 2 * L, A.cand_lens + 2 * (idx - A.n_nodes), L);
+                                      ? (A.root_of[idx] == my_root && ball_same(me, cl, A.nodes + idx * 2 * L, A.lens + 2 * idx, L))
+                                      : (A.root_of[A.lo + (idx - A.n_nodes) / A.K] == my_root &&
+                                         ball_same(me, cl, A.cand + (idx - A.n_nodes) * 2 * L, A.cand_lens + 2 * (idx - A.n_nodes), L));
                 if (same) {
                     if (idx >= A.n_nodes) atomicMin((unsigned long long*)&A.table[s], (unsigned long long)mine);
                     my_slot = (uint32_t)s;
@@ -282,6 +285,7 @@ __global__ void __launch_bounds__(kBallThreads) ball_commit_kernel(const BallArg
         A.lens[2 * node] = (uint16_t)l1;
         A.lens[2 * node + 1] = (uint16_t)l2;
         A.level[node] = (uint8_t)next_level;
+        A.root_of[node] = A.root_of[A.lo + c / A.K];
     }
 }
 // second pass (after every winner's rank is final): re-point the table slots at the nodes
@@ -333,6 +337,23 @@ __global__ void __launch_bounds__(1024) ball_edges_kernel(const BallArgs A, uint
     if (threadIdx.x == 0) A.ctrl[2] = carry;
 }
 
+// the start presentations (nodes 0 .. n_roots-1) enter the visited table
+__global__ void __launch_bounds__(256) ball_roots_kernel(const BallArgs A, int n_roots) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_roots) return;
+    const int8_t* row = A.nodes + (uint64_t)r * 2 * A.L;
+    const uint64_t h = ball_hash(row, A.lens[2 * r], row + A.L, A.lens[2 * r + 1], (uint32_t)r);
+    const unsigned long long v = ((h >> 40) << 40) | (unsigned long long)(r + 1);
+    for (uint64_t s = h & A.tmask;; s = (s + 1) & A.tmask)  // distinct (root, state) keys: plain linear probing
+        if (atomicCAS((unsigned long long*)&A.table[s], 0ull, v) == 0ull) break;
+}
+
+// nodes per start presentation
+__global__ void __launch_bounds__(256) ball_count_kernel(const uint32_t* root_of, uint64_t n, unsigned long long* counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&counts[root_of[i]], 1ull);
+}
+
 }  // namespace acs
 
 using namespace acs;
@@ -354,52 +375,55 @@ int ball_fail(int code, const std::string& m) {
     } while (0)
 }  // namespace
 
-extern "C" {
+namespace {
 
-/* Explores the AC graph of the barcode_analysis state model breadth first from (r1, r2).
- *   radius >= 0 : all states within `radius` moves (neibourhoods.cpp:18-54); size_cap == 0
- *   size_cap > 0: all states of total length <= size_cap reachable through such states
- *                 (ac_bfs.cpp:36-91, radius < 0 = unbounded)
- * h_letters: r1 then r2 as int8 letters (lengths len1, len2), classic = 14 moves, else the 12 prime moves.
- * Outputs (any may be NULL): *n_nodes; node sizes / levels in discovery order (capacity cap_nodes);
- * edges (cn, cc, filtration) triples in the reference's output order (capacity cap_edges), *n_edges.
- * Returns ACS_ERR_NOMEM if max_nodes is exceeded. */
-int acs_ball_explore(int device, const int8_t* h_letters, int len1, int len2, int radius, int size_cap, int classic,
-                     int64_t max_nodes, int64_t* n_nodes_out, uint16_t* h_sizes, uint8_t* h_levels, int64_t cap_nodes,
-                     uint32_t* h_edges, int64_t cap_edges, int64_t* n_edges_out) {
-    if (!h_letters || len1 < 0 || len2 < 0 || max_nodes < 1) return ball_fail(ACS_ERR_INVALID, "ball: bad argument");
+// Breadth-first exploration from n_roots start presentations at once (each node carries its root's index, and
+// the visited set is keyed by (root, state), so the runs are independent but share every kernel launch).
+// Root r: letters h_letters[off[2r] .. off[2r+1]) and [off[2r+1] .. off[2r+2]).
+int ball_run(int device, const int8_t* h_letters, const int64_t* off, int n_roots, int radius, int size_cap, int classic,
+             int64_t max_nodes, int64_t* n_nodes_out, int64_t* h_counts, uint16_t* h_sizes, uint8_t* h_levels,
+             int64_t cap_nodes, uint32_t* h_edges, int64_t cap_edges, int64_t* n_edges_out) {
+    if (!h_letters || !off || n_roots < 1 || max_nodes < n_roots) return ball_fail(ACS_ERR_INVALID, "ball: bad argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
         return ball_fail(ACS_ERR_NO_DEVICE, "no CUDA device visible; there is no CPU fallback");
     }
     if (cudaSetDevice(device) != cudaSuccess) return ball_fail(ACS_ERR_CUDA, "ball: cudaSetDevice");
-    for (int i = 0; i < len1 + len2; ++i)
+    int max_len = 1;
+    for (int r = 0; r < n_roots; ++r) {
+        const int64_t a = off[2 * r], b = off[2 * r + 1], c = off[2 * r + 2];
+        if (a > b || b > c) return ball_fail(ACS_ERR_INVALID, "ball: offsets must be non-decreasing");
+        max_len = std::max<int>(max_len, (int)std::max(b - a, c - b));
+    }
+    for (int64_t i = 0; i < off[2 * n_roots]; ++i)
         if (h_letters[i] == 0 || h_letters[i] < -2 || h_letters[i] > 2) return ball_fail(ACS_ERR_INVALID, "ball: letters must be +-1, +-2");
     const int K = classic ? 14 : 12;
     // stride: a relator at most doubles per move (concatenation); radius-bounded runs size it from the start
-    int L = size_cap > 0 ? size_cap : std::max(len1, len2);
+    int L = size_cap > 0 ? size_cap : max_len;
     if (size_cap <= 0) {
-        int a = std::max(len1, 1), b = std::max(len2, 1);
+        int a = max_len, b = max_len;
         for (int r = 0; r < std::max(radius, 0); ++r) {  // concatenation adds the other relator, conjugation 2 letters
-            const int s = std::max(a + b, std::max(a, b) + 2);
+            const int s2 = std::max(a + b, std::max(a, b) + 2);
             b = std::max(a, b);
-            a = s;
+            a = s2;
         }
         L = std::max(a, b) + 2;
     }
     L = (std::min(std::max(L, 4), 512) + 3) / 4 * 4;
     const uint64_t cap = (uint64_t)max_nodes + 16;
     uint64_t tcap = 1024;
-    const uint64_t chunk = 8192;
+    const uint64_t chunk = n_roots > 1 ? 32768 : 8192;
     const uint64_t ccap = chunk * K;
     while (tcap < 2 * (cap + ccap)) tcap <<= 1;  // committed nodes + the tentative entries of one chunk, half full
     BallArgs A{};
     uint32_t* d_edges = nullptr;
+    unsigned long long* d_counts = nullptr;
     auto free_all = [&]() {
         cudaFree(A.nodes);
         cudaFree(A.lens);
         cudaFree(A.level);
+        cudaFree(A.root_of);
         cudaFree(A.table);
         cudaFree(A.cand);
         cudaFree(A.cand_lens);
@@ -409,10 +433,12 @@ int acs_ball_explore(int device, const int8_t* h_letters, int len1, int len2, in
         cudaFree(A.win);
         cudaFree(A.ctrl);
         cudaFree(d_edges);
+        cudaFree(d_counts);
     };
     BALL_CUDA(cudaMalloc((void**)&A.nodes, cap * 2 * L));
     BALL_CUDA(cudaMalloc((void**)&A.lens, cap * 4));
     BALL_CUDA(cudaMalloc((void**)&A.level, cap));
+    BALL_CUDA(cudaMalloc((void**)&A.root_of, cap * 4));
     BALL_CUDA(cudaMalloc((void**)&A.table, tcap * 8));
     BALL_CUDA(cudaMalloc((void**)&A.cand, ccap * 2 * L));
     BALL_CUDA(cudaMalloc((void**)&A.cand_lens, ccap * 4));
@@ -432,45 +458,44 @@ int acs_ball_explore(int device, const int8_t* h_letters, int len1, int len2, in
     A.want_edges = want_edges ? 1 : 0;
     BALL_CUDA(cudaMemset(A.table, 0, tcap * 8));
     BALL_CUDA(cudaMemset(A.ctrl, 0, 32));
-    // root: the sorted pair (sort_, AC_UTILS_no_hash.cpp:131-147)
+    // roots: the sorted pairs (sort_, AC_UTILS_no_hash.cpp:131-147) as nodes 0 .. n_roots-1, level 0
     {
-        std::vector<int8_t> root((size_t)2 * L, 0);
-        const int8_t* x = h_letters;
-        const int8_t* y = h_letters + len1;
+        std::vector<int8_t> rows((size_t)n_roots * 2 * L, 0);
+        std::vector<uint16_t> lens((size_t)n_roots * 2);
+        std::vector<uint32_t> roots((size_t)n_roots);
         auto less = [](const int8_t* p, int lp, const int8_t* q, int lq) {
             if (lp != lq) return lp < lq;
             for (int i = 0; i < lp; ++i)
                 if (p[i] != q[i]) return p[i] < q[i];
             return false;
         };
-        const bool keep = less(x, len1, y, len2);
-        const int8_t* f = keep ? x : y;
-        const int lf = keep ? len1 : len2;
-        const int8_t* s = keep ? y : x;
-        const int ls = keep ? len2 : len1;
-        if (lf > L || ls > L) {
-            free_all();
-            return ball_fail(ACS_ERR_UNSUPPORTED, "ball: relators longer than 512 letters are not supported");
+        for (int r = 0; r < n_roots; ++r) {
+            const int8_t* x = h_letters + off[2 * r];
+            const int8_t* y = h_letters + off[2 * r + 1];
+            const int len1 = (int)(off[2 * r + 1] - off[2 * r]), len2 = (int)(off[2 * r + 2] - off[2 * r + 1]);
+            const bool keep = less(x, len1, y, len2);
+            const int8_t* f = keep ? x : y;
+            const int lf = keep ? len1 : len2;
+            const int8_t* sd = keep ? y : x;
+            const int ls = keep ? len2 : len1;
+            if (lf > L || ls > L) {
+                free_all();
+                return ball_fail(ACS_ERR_UNSUPPORTED, "ball: relators longer than 512 letters are not supported");
+            }
+            int8_t* row = rows.data() + (size_t)r * 2 * L;
+            std::memcpy(row, f, lf);
+            std::memcpy(row + L, sd, ls);
+            lens[2 * r] = (uint16_t)lf;
+            lens[2 * r + 1] = (uint16_t)ls;
+            roots[r] = (uint32_t)r;
         }
-        std::memcpy(root.data(), f, lf);
-        std::memcpy(root.data() + L, s, ls);
-        const uint16_t lens[2] = {(uint16_t)lf, (uint16_t)ls};
-        const uint8_t lvl = 0;
-        BALL_CUDA(cudaMemcpy(A.nodes, root.data(), (size_t)2 * L, cudaMemcpyHostToDevice));
-        BALL_CUDA(cudaMemcpy(A.lens, lens, 4, cudaMemcpyHostToDevice));
-        BALL_CUDA(cudaMemcpy(A.level, &lvl, 1, cudaMemcpyHostToDevice));
-        // same hash as the device: FNV over the two byte strings
-        uint64_t h = 0xcbf29ce484222325ull ^ ((uint64_t)lf << 32 | (uint64_t)ls);
-        for (int i = 0; i < lf; ++i) h = (h ^ (uint8_t)f[i]) * 0x100000001b3ull;
-        h = (h ^ 0xFF) * 0x100000001b3ull;
-        for (int i = 0; i < ls; ++i) h = (h ^ (uint8_t)s[i]) * 0x100000001b3ull;
-        h ^= h >> 29;
-        h *= 0xbf58476d1ce4e5b9ull;
-        h ^= h >> 32;
-        const uint64_t v = ((h >> 40) << 40) | 1ull;
-        BALL_CUDA(cudaMemcpy(A.table + (h & A.tmask), &v, 8, cudaMemcpyHostToDevice));
+        BALL_CUDA(cudaMemcpy(A.nodes, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+        BALL_CUDA(cudaMemcpy(A.lens, lens.data(), lens.size() * 2, cudaMemcpyHostToDevice));
+        BALL_CUDA(cudaMemset(A.level, 0, n_roots));
+        BALL_CUDA(cudaMemcpy(A.root_of, roots.data(), roots.size() * 4, cudaMemcpyHostToDevice));
+        ball_roots_kernel<<<(n_roots + 255) / 256, 256>>>(A, n_roots);
     }
-    uint64_t n_nodes = 1, head = 0, level_end = 1;
+    uint64_t n_nodes = (uint64_t)n_roots, head = 0, level_end = (uint64_t)n_roots;
     int level = 0;
     int64_t n_edges = 0;
     while (head < n_nodes) {
@@ -514,6 +539,12 @@ int acs_ball_explore(int device, const int8_t* h_letters, int len1, int len2, in
     }
     if (n_nodes_out) *n_nodes_out = (int64_t)n_nodes;
     if (n_edges_out) *n_edges_out = n_edges;
+    if (h_counts) {
+        BALL_CUDA(cudaMalloc((void**)&d_counts, (size_t)n_roots * 8));
+        BALL_CUDA(cudaMemset(d_counts, 0, (size_t)n_roots * 8));
+        ball_count_kernel<<<(unsigned)((n_nodes + 255) / 256), 256>>>(A.root_of, n_nodes, d_counts);
+        BALL_CUDA(cudaMemcpy(h_counts, d_counts, (size_t)n_roots * 8, cudaMemcpyDeviceToHost));
+    }
     const uint64_t ncopy = std::min<uint64_t>(n_nodes, (uint64_t)std::max<int64_t>(cap_nodes, 0));
     if (h_sizes && ncopy) {
         std::vector<uint16_t> lens(2 * ncopy);
@@ -523,6 +554,38 @@ int acs_ball_explore(int device, const int8_t* h_letters, int len1, int len2, in
     if (h_levels && ncopy) BALL_CUDA(cudaMemcpy(h_levels, A.level, ncopy, cudaMemcpyDeviceToHost));
     free_all();
     return ACS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* Explores the AC graph of the barcode_analysis state model breadth first from (r1, r2).
+ *   radius >= 0 : all states within `radius` moves (neibourhoods.cpp:18-54); size_cap == 0
+ *   size_cap > 0: all states of total length <= size_cap reachable through such states
+ *                 (ac_bfs.cpp:36-91, radius < 0 = unbounded)
+ * h_letters: r1 then r2 as int8 letters (lengths len1, len2), classic = 14 moves, else the 12 prime moves.
+ * Outputs (any may be NULL): *n_nodes; node sizes / levels in discovery order (capacity cap_nodes);
+ * edges (cn, cc, filtration) triples in the reference's output order (capacity cap_edges), *n_edges.
+ * Returns ACS_ERR_NOMEM if max_nodes is exceeded. */
+int acs_ball_explore(int device, const int8_t* h_letters, int len1, int len2, int radius, int size_cap, int classic,
+                     int64_t max_nodes, int64_t* n_nodes_out, uint16_t* h_sizes, uint8_t* h_levels, int64_t cap_nodes,
+                     uint32_t* h_edges, int64_t cap_edges, int64_t* n_edges_out) {
+    if (!h_letters || len1 < 0 || len2 < 0 || max_nodes < 1) return ball_fail(ACS_ERR_INVALID, "ball: bad argument");
+    const int64_t off[3] = {0, len1, (int64_t)len1 + len2};
+    return ball_run(device, h_letters, off, 1, radius, size_cap, classic, max_nodes, n_nodes_out, nullptr, h_sizes, h_levels,
+                    cap_nodes, h_edges, cap_edges, n_edges_out);
+}
+
+/* neibourhoods.cpp read_do_and_write (:58-103) for a whole input file at once: the radius-`radius` ball sizes of
+ * n_roots presentations in ONE exploration (all balls advance level by level in the same kernel launches).
+ * Root r = letters [h_off[2r], h_off[2r+1]) and [h_off[2r+1], h_off[2r+2]) of h_letters; h_counts[n_roots].
+ * max_nodes bounds the SUM of the ball sizes (ACS_ERR_NOMEM if exceeded: split the batch). */
+int acs_ball_sizes(int device, const int8_t* h_letters, const int64_t* h_off, int n_roots, int radius, int classic,
+                   int64_t max_nodes, int64_t* h_counts) {
+    if (!h_counts || radius < 0) return ball_fail(ACS_ERR_INVALID, "ball: bad argument");
+    return ball_run(device, h_letters, h_off, n_roots, radius, 0, classic, max_nodes, nullptr, h_counts, nullptr, nullptr, 0,
+                    nullptr, 0, nullptr);
 }
 
 }  // extern "C"

@@ -64,6 +64,8 @@ constexpr int kCtrlWords = 136;        // sol, err, first_len[128], log end, ier
 constexpr int kCtrlSol = 0, kCtrlErr = 1, kCtrlLen0 = 2, kCtrlCount = 130, kCtrlIerr = 131, kCtrlStart = 132;
 // table slot: 23-bit fingerprint << 40 | (record-log position + 1); 0 = empty
 constexpr uint64_t kPosMask = (1ull << 40) - 1;
+// the per-destination log cursors are hot atomics: one per 256 bytes, so that they sit in different L2 lines / slices
+constexpr int kCurStride = 32;
 constexpr int kScanT = 256, kScanPer = 8, kScanBlock = kScanT * kScanPer;  // words per scan block
 
 enum : int { IERR_LOG_FULL = 1, IERR_TABLE_FULL = 2, IERR_SHARD_FULL = 4, IERR_TIMEOUT = 8 };
@@ -94,7 +96,7 @@ struct PbShard {
     uint64_t* nodes;     // [cap][2W+2]  owned nodes in FIFO order: key words, parent link, global id
     uint64_t* table;     // [tmask+1]
     uint4* rt;           // [words+1] rank table: {global prefix, global bits, local prefix, local bits}
-    unsigned long long* cursors;     // [world] append positions in the peers' record logs (persist over a run)
+    unsigned long long* cursors;     // [world * kCurStride] append positions in the peers' record logs (persist over a run)
     unsigned long long* cstart;      // [world] their values at the start of the current chunk
     unsigned long long* ctrl_local;  // [kCtrlWords]
     // arena (same layout on every rank)
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(256) pb_prep_kernel(const PbShard S) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (int64_t)gridDim.x * blockDim.x)
         bm[i] = 0;
     if (blockIdx.x != 0) return;
-    if (threadIdx.x < S.world) S.cstart[threadIdx.x] = S.cursors[threadIdx.x];
+    if (threadIdx.x < S.world) S.cstart[threadIdx.x] = S.cursors[threadIdx.x * kCurStride];
     if (threadIdx.x < kCtrlWords)
         S.ctrl_local[threadIdx.x] = (threadIdx.x == kCtrlCount || threadIdx.x == kCtrlIerr) ? 0ull : ~0ull;
     if (threadIdx.x == 0) {
@@ -364,7 +366,7 @@ __device__ __noinline__ void pb_flush(const PbShard& S, const DestBase* DB, int 
             Q.off[lane] = x - cnt;
             unsigned long long pos = ~0ull;
             if (cnt) {
-                pos = atomicAdd(&S.cursors[lane], (unsigned long long)cnt);
+                pos = atomicAdd(&S.cursors[lane * kCurStride], (unsigned long long)cnt);
                 if (pos + cnt > (unsigned long long)log_cap) {
                     atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_LOG_FULL);
                     pos = ~0ull;
@@ -500,6 +502,202 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
     if (lane == 0 && sent) atomicAdd(&S.st->records_sent, sent);
 }
 
+// ---- expand, block-level staging (world > 1) -------------------------------------------------
+// The per-warp flush above sends ~16 records per destination at a time: 256-byte key runs and
+// 64-byte id runs at arbitrary alignment, i.e. NVLink write packets of ~60 bytes with byte enables.
+// Here the whole block stages the children of kCtaMoves moves of its 32*warps parents (up to
+// 32*warps*kCtaMoves records), sorts them by destination rank with a counting sort over all
+// threads and sends one run per destination: ~1 KB of keys per run on the AC(3) workload, mostly
+// whole 128-byte lines.  Same records, same logs, same cursors as the per-warp path.
+constexpr int kCtaMoves = 4;  // moves per flush (the 12-move loop is unrolled by the same factor)
+template <int W>
+__host__ __device__ constexpr int cta_stage_bytes(int warps) {
+    // keys | candidate ids | sorted order (u16) | destination (u8) | counters
+    return warps * 32 * kCtaMoves * (16 * W + 4 + 2 + 1) + kPbMaxWorld * (4 + 4 + 8) + 16;
+}
+template <int W>
+struct CtaStage {
+    ulonglong2* keys;
+    uint32_t* c;
+    uint16_t* perm;
+    uint8_t* dest;
+    unsigned long long* gpos;
+    uint32_t* cnt;
+    uint32_t* off;
+    uint32_t* total;
+    __device__ __forceinline__ explicit CtaStage(int warps) {
+        const int cap = warps * 32 * kCtaMoves;
+        unsigned char* p = pb_smem;
+        keys = reinterpret_cast<ulonglong2*>(p);
+        p += (size_t)cap * 16 * W;
+        gpos = reinterpret_cast<unsigned long long*>(p);
+        p += kPbMaxWorld * 8;
+        c = reinterpret_cast<uint32_t*>(p);
+        p += (size_t)cap * 4;
+        cnt = reinterpret_cast<uint32_t*>(p);
+        p += kPbMaxWorld * 4;
+        off = reinterpret_cast<uint32_t*>(p);
+        p += kPbMaxWorld * 4;
+        total = reinterpret_cast<uint32_t*>(p);
+        p += 16;
+        perm = reinterpret_cast<uint16_t*>(p);
+        p += (size_t)cap * 2;
+        dest = p;
+    }
+};
+
+// all threads of the block; *Q.total records are staged.  Leaves *Q.total == 0 and cnt[] == 0.
+template <int W>
+__device__ __forceinline__ void pb_flush_cta(const PbShard& S, const DestBase* DB, const CtaStage<W>& Q, int64_t log_cap,
+                                             int world) {
+    constexpr int kMaxPer = kCtaMoves;  // records per thread: cap / threads = 32*warps*kCtaMoves / (32*warps)
+    __syncthreads();  // every warp's records of this batch are staged
+    const uint32_t n = *Q.total;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    uint32_t d[kMaxPer], rk[kMaxPer];
+#pragma unroll
+    for (int r = 0; r < kMaxPer; ++r) {
+        const uint32_t idx = r * nt + tid;
+        d[r] = 0;
+        rk[r] = 0;
+        if (idx < n) {
+            d[r] = Q.dest[idx];
+            rk[r] = atomicAdd(&Q.cnt[d[r]], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const uint32_t cnt = tid < world ? Q.cnt[tid] : 0u;
+        uint32_t x = cnt;
+#pragma unroll
+        for (int o = 1; o < kPbMaxWorld; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (tid >= o) x += t;
+        }
+        if (tid < world) {
+            Q.off[tid] = x - cnt;
+            unsigned long long pos = ~0ull;
+            if (cnt) {
+                pos = atomicAdd(&S.cursors[tid * kCurStride], (unsigned long long)cnt);
+                if (pos + cnt > (unsigned long long)log_cap) {
+                    atomicOr(&S.ctrl_local[kCtrlIerr], (unsigned long long)IERR_LOG_FULL);
+                    pos = ~0ull;
+                }
+            }
+            Q.gpos[tid] = pos;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kMaxPer; ++r) {
+        const uint32_t idx = r * nt + tid;
+        if (idx < n) Q.perm[Q.off[d[r]] + rk[r]] = (uint16_t)idx;
+    }
+    __syncthreads();
+    if (tid < kPbMaxWorld) Q.cnt[tid] = 0;  // for the next flush (read again only after its first barrier)
+    if (tid == 0) *Q.total = 0;
+    for (uint32_t t = tid; t < n; t += nt) {
+        const uint32_t idx = Q.perm[t];
+        const uint32_t dd = Q.dest[idx];
+        const unsigned long long pos = Q.gpos[dd];
+        if (pos != ~0ull) {
+            const unsigned long long o = pos + (t - Q.off[dd]);
+            ulonglong2* dk = DB->keys[dd] + o * W;
+#pragma unroll
+            for (int i = 0; i < W; ++i) dk[i] = Q.keys[idx * W + i];
+            DB->c[dd][o] = Q.c[idx];
+        }
+    }
+    __syncthreads();  // the staging area is free again
+}
+
+template <int W, bool TRUSTED>
+__global__ void __launch_bounds__(256) pb_expand_cta_kernel(const PbShard S) {
+    const PbState* st = S.st;
+    if (st->done) return;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int world = S.world;
+    __shared__ DestBase DB;
+    const int64_t l1 = st->l1, log_cap = st->log_cap;
+    CtaStage<W> Q(warps);
+    if (threadIdx.x < world) {
+        char* base = S.peer[threadIdx.x];
+        DB.keys[threadIdx.x] = reinterpret_cast<ulonglong2*>(sh_keys(S, base)) + (int64_t)S.rank * log_cap * W;
+        DB.c[threadIdx.x] = sh_c(S, base) + (int64_t)S.rank * log_cap;
+    }
+    if (threadIdx.x < kPbMaxWorld) Q.cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *Q.total = 0;
+    __syncthreads();
+    const uint64_t head = (uint64_t)st->head;
+    const int mrl = st->mrl;
+    const bool cyc = st->cyclical != 0;
+    const int min_len = st->min_len;
+    const uint32_t lt = (1u << lane) - 1u;
+    unsigned long long sent = 0;
+    // block-uniform trip count: the block's 32*warps consecutive parents per round
+    for (int64_t bbase = st->l0 + (int64_t)blockIdx.x * 32 * warps; bbase < l1; bbase += (int64_t)gridDim.x * 32 * warps) {
+        const int64_t j = bbase + 32 * wib + lane;
+        const bool valid = j < l1;
+        Key<W> pk;
+#pragma unroll
+        for (int i = 0; i < 2 * W; ++i) pk.k[i] = 0;
+        uint64_t pg = 0;
+        int back = -1;  // see pb_expand_kernel
+        if (valid) {
+            int64_t pl, gj;
+            node_load<W>(S.nodes, (uint64_t)j, pk, pl, gj);
+            pg = (uint64_t)gj;
+            if (TRUSTED && !cyc) {
+                if (pl >= 16) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
+            }
+        }
+        Rel<2 * W> p0, p1;
+        split_key<W>(pk, p0, p1);
+        const uint32_t cbase = (uint32_t)((pg - head) * 12);
+        const uint64_t gbase = pg * 12;
+#pragma unroll 1
+        for (int a0 = 0; a0 < 12; a0 += kCtaMoves) {
+#pragma unroll
+            for (int aa = 0; aa < kCtaMoves; ++aa) {
+                const int a = a0 + aa;
+                Rel<2 * W> r0 = p0, r1 = p1;
+                bool emit = false;
+                Key<W> child;
+#pragma unroll
+                for (int i = 0; i < 2 * W; ++i) child.k[i] = 0;
+                if (valid && a != back) {
+                    bool co;
+                    const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
+                    if (stt != ST_OK) {
+                        atomicMin(&S.ctrl_local[kCtrlErr], (unsigned long long)(((gbase + a) << 2) | (unsigned)stt));
+                    } else {
+                        const int L = r0.len + r1.len;
+                        if (L < min_len) atomicMin(&S.ctrl_local[kCtrlLen0 + L], (unsigned long long)(gbase + a));
+                        if (L == 2) atomicMin(&S.ctrl_local[kCtrlSol], (unsigned long long)(gbase + a));  // before the visited test
+                        child = make_key<W>(r0, r1);
+                        emit = !key_eq<W>(child, pk);
+                    }
+                }
+                const uint32_t act = __ballot_sync(0xFFFFFFFFu, emit);
+                uint32_t wbase = 0;
+                if (lane == 0 && act) wbase = atomicAdd(Q.total, (uint32_t)__popc(act));
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                if (emit) {
+                    const uint32_t q = wbase + __popc(act & lt);
+#pragma unroll
+                    for (int i = 0; i < W; ++i) Q.keys[q * W + i] = make_ulonglong2(child.k[2 * i], child.k[2 * i + 1]);
+                    Q.c[q] = cbase + a;
+                    Q.dest[q] = (uint8_t)pb_owner<W>(child, world);
+                }
+                sent += __popc(act);
+            }
+            pb_flush_cta<W>(S, &DB, Q, log_cap, world);
+        }
+    }
+    __threadfence_system();
+    if (lane == 0 && sent) atomicAdd(&S.st->records_sent, sent);
+}
+
 // ---- signal / wait ---------------------------------------------------------------------------
 // kind 0: "my records and control block for this chunk are in your inbox"
 // kind 1: "my winner bitmap for this chunk is final"
@@ -511,7 +709,7 @@ __global__ void __launch_bounds__(256) pb_signal_kernel(const PbShard S, int kin
         for (int i = threadIdx.x; i < world * kCtrlWords; i += blockDim.x) {
             const int d = i / kCtrlWords, w = i % kCtrlWords;
             unsigned long long v = S.ctrl_local[w];
-            if (w == kCtrlCount) v = S.cursors[d];
+            if (w == kCtrlCount) v = S.cursors[d * kCurStride];
             if (w == kCtrlStart) v = S.cstart[d];
             if (w == kCtrlIerr) v |= (unsigned long long)st->ierr;
             sh_ctrl(S, S.peer[d], st->buf, S.rank)[w] = v;
@@ -561,13 +759,6 @@ __device__ __forceinline__ void load_regions(const PbShard& S, const PbState* st
     }
     __syncthreads();
 }
-// virtual record index v (0 <= v < total) -> position in this rank's record log
-__device__ __forceinline__ int64_t region_index(const RegionMap* R, int world, int64_t log_cap, unsigned long long v) {
-    int s = 0;
-#pragma unroll 1
-    for (int k = 1; k < world; ++k) s += (v >= R->vstart[k]) ? 1 : 0;
-    return (int64_t)s * log_cap + (int64_t)(R->cstart[s] + (v - R->vstart[s]));
-}
 // does log position p belong to the current chunk (a tentative entry)?
 __device__ __forceinline__ bool is_tentative(const RegionMap* R, int world, int64_t log_cap, uint64_t p) {
     int s = 0;
@@ -601,9 +792,14 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
     uint32_t* bm = sh_bitmap(S, S.arena, st->buf);
     const uint64_t tmask = st->tmask;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->records_recv += total;
-    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+    // source by source (no per-record search for the source region); the grid offset rotates with the
+    // source so that the tail of one region and the head of the next keep all blocks busy
+    for (int src = 0; src < world; ++src) {
+    const unsigned long long n_src = R.vstart[src + 1] - R.vstart[src];
+    const int64_t base_src = (int64_t)src * log_cap + (int64_t)R.cstart[src];
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_src;
          v += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t i = region_index(&R, world, log_cap, v);
+        const int64_t i = base_src + (int64_t)v;
         const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
         const uint32_t c = __ldcg(in_c + i);
         const uint64_t h = pb_hash<W>(key);
@@ -658,6 +854,7 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
                 }
             }
         }
+    }
     }
 }
 
@@ -728,15 +925,25 @@ __global__ void __launch_bounds__(kScanT) pb_scan_sums_kernel(const PbShard S) {
             sl += __popc(g[k]);
         }
         if (combine) {
-            // all peer loads of the block are issued before the first one is consumed
-            for (int r = 0; r < S.world; ++r) {
-                if (r == S.rank) continue;
-                const uint32_t* pb = sh_bitmap(S, S.peer[r], st->buf);
+            // peer loads in batches of four ranks: 32 independent NVLink loads per thread are in flight
+            // before the first one is consumed (one round trip per batch instead of one per peer)
+            for (int r0 = 0; r0 < S.world; r0 += 4) {
+                uint32_t t[4][kScanPer];
 #pragma unroll
-                for (int k = 0; k < kScanPer; ++k) {
-                    const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
-                    if (i < nwords) g[k] |= __ldcv(pb + i);
+                for (int q = 0; q < 4; ++q) {
+                    const int r = r0 + q;
+                    const bool on = r < S.world && r != S.rank;
+                    const uint32_t* pb = sh_bitmap(S, S.peer[on ? r : S.rank], st->buf);
+#pragma unroll
+                    for (int k = 0; k < kScanPer; ++k) {
+                        const int64_t i = b * kScanBlock + (int64_t)k * kScanT + threadIdx.x;
+                        t[q][k] = (on && i < nwords) ? __ldcv(pb + i) : 0u;
+                    }
                 }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int k = 0; k < kScanPer; ++k) g[k] |= t[q][k];
             }
             for (int r = 0; r < S.world; ++r) {
                 uint32_t* pg = sh_bmg(S, S.peer[r]);
@@ -971,9 +1178,13 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
     const uint64_t limit = (uint64_t)st->limit;
     const uint64_t n_nodes0 = (uint64_t)st->n_nodes0, n_local0 = (uint64_t)st->n_local0;
     const uint64_t head0 = (uint64_t)st->head0;
-    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+    (void)total;
+    for (int src = 0; src < S.world; ++src) {  // source by source: no per-record search for the source region
+    const unsigned long long n_src = R.vstart[src + 1] - R.vstart[src];
+    const int64_t base_src = (int64_t)src * log_cap + (int64_t)R.cstart[src];
+    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_src;
          v += (unsigned long long)gridDim.x * blockDim.x) {
-        const int64_t i = region_index(&R, S.world, log_cap, v);
+        const int64_t i = base_src + (int64_t)v;
         const uint64_t c = __ldcg(in_c + i);
         if (c >= limit) continue;
         const uint4 e = S.rt[c >> 5];
@@ -984,6 +1195,7 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
         if (idx >= (uint64_t)st->cap_local) continue;  // IERR_SHARD_FULL was raised by decide
         node_store<W>(S.nodes, idx, load_key_cg<W>(in_keys, (uint64_t)i), (int64_t)(((head0 + c / 12) << 4) | (c % 12)),
                       (int64_t)g);
+    }
     }
 }
 
@@ -1118,6 +1330,9 @@ struct acs_pbfs {
     int sms = 148;
     int expand_wpb = 8, expand_blocks = 148, insert_blocks = 148, commit_blocks = 148;
     size_t expand_smem = 0;
+    bool cta_stage = false;  // block-level staging of the expansion (world > 1; ACS_PBFS_CTA_STAGE=0 disables)
+    int cta_blocks = 148, cta_threads = 256;
+    size_t cta_smem = 0;
     int32_t* d_path = nullptr;
     int path_cap = 1 << 16;
     long long* d_small = nullptr;
@@ -1214,7 +1429,7 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     PB_ALLOC(S.nodes, (size_t)b->cap_local * 8 * (2 * b->W + 2));
     PB_ALLOC(S.table, (size_t)b->tcap * 8);
     PB_ALLOC(S.rt, (size_t)(S.bitmap_words + 1) * sizeof(uint4));
-    PB_ALLOC(S.cursors, kPbMaxWorld * 8);
+    PB_ALLOC(S.cursors, kPbMaxWorld * kCurStride * 8);
     PB_ALLOC(S.cstart, kPbMaxWorld * 8);
     PB_ALLOC(S.ctrl_local, kCtrlWords * 8);
     PB_ALLOC(b->d_path, (size_t)b->path_cap * 2 * sizeof(int32_t) + 16);
@@ -1250,6 +1465,23 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     if (b->W == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_expand_kernel<1, true>, 32 * wpb, b->expand_smem);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pb_expand_kernel<2, true>, 32 * wpb, b->expand_smem);
     b->expand_blocks = b->sms * std::max(per_sm, 1);
+    {
+        const char* e2 = std::getenv("ACS_PBFS_CTA_STAGE");
+        b->cta_stage = world > 1 && !(e2 && e2[0] == '0');
+        b->cta_threads = 256;
+        b->cta_smem = b->W == 1 ? cta_stage_bytes<1>(b->cta_threads / 32) : cta_stage_bytes<2>(b->cta_threads / 32);
+        int cps = 1;
+        if (b->W == 1) {
+            cudaFuncSetAttribute(pb_expand_cta_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->cta_smem);
+            cudaFuncSetAttribute(pb_expand_cta_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->cta_smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, pb_expand_cta_kernel<1, true>, b->cta_threads, b->cta_smem);
+        } else {
+            cudaFuncSetAttribute(pb_expand_cta_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->cta_smem);
+            cudaFuncSetAttribute(pb_expand_cta_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->cta_smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, pb_expand_cta_kernel<2, true>, b->cta_threads, b->cta_smem);
+        }
+        b->cta_blocks = b->sms * std::max(cps, 1);
+    }
     // persistent grid-stride kernels: exactly one wave of resident blocks
     int ib = 1, cb = 1;
     if (b->W == 1) {
@@ -1389,7 +1621,7 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
         PB_CUDA(cudaSetDevice(b->device));
         cudaStream_t s = stream_of(b);
         PB_CUDA(cudaMemsetAsync(b->S.table, 0, b->tcap * sizeof(uint64_t), s));
-        PB_CUDA(cudaMemsetAsync(b->S.cursors, 0, kPbMaxWorld * 8, s));
+        PB_CUDA(cudaMemsetAsync(b->S.cursors, 0, kPbMaxWorld * kCurStride * 8, s));
         PbState st{};
         st.budget = b->budget;
         st.cap_local = b->cap_local;
@@ -1427,7 +1659,7 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
             PB_CUDA(cudaMemcpyAsync(b->S.nodes, node0, sizeof(node0), cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(arena + b->S.off_keys + log_pos * sizeof(root), &root, sizeof(root), cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(arena + b->S.off_c + log_pos * 4, &c0, 4, cudaMemcpyHostToDevice, s));
-            PB_CUDA(cudaMemcpyAsync(b->S.cursors + owner, &one, 8, cudaMemcpyHostToDevice, s));
+            PB_CUDA(cudaMemcpyAsync(b->S.cursors + owner * kCurStride, &one, 8, cudaMemcpyHostToDevice, s));
             PB_CUDA(cudaMemcpyAsync(b->S.table + ((h & (b->tcap - 1)) & ~3ull), &slot_val, 8, cudaMemcpyHostToDevice, s));
         }
         PB_CUDA(cudaStreamSynchronize(s));  // the staging copies above read host stack memory
@@ -1474,7 +1706,13 @@ int pb_run_impl(acs_pbfs** sh, int n_local, const int8_t* h_presentation, int32_
     if (rc != ACS_OK) return rc;                             \
     mark();
         PB_PHASE((pb_prep_kernel<<<b->sms * 2, 256, 0, s>>>(b->S)));
-        if (chunk == 0) {
+        if (b0->cta_stage) {
+            if (chunk == 0) {
+                PB_PHASE((pb_expand_cta_kernel<W, false><<<b->cta_blocks, b->cta_threads, b->cta_smem, s>>>(b->S)));
+            } else {
+                PB_PHASE((pb_expand_cta_kernel<W, true><<<b->cta_blocks, b->cta_threads, b->cta_smem, s>>>(b->S)));
+            }
+        } else if (chunk == 0) {
             PB_PHASE((pb_expand_kernel<W, false><<<b->expand_blocks, 32 * b->expand_wpb, b->expand_smem, s>>>(b->S, b->expand_wpb)));
         } else {
             PB_PHASE((pb_expand_kernel<W, true><<<b->expand_blocks, 32 * b->expand_wpb, b->expand_smem, s>>>(b->S, b->expand_wpb)));

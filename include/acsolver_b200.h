@@ -298,6 +298,35 @@ void acs_pbfs_destroy(acs_pbfs *b);
 int acs_ball_explore(int device, const int8_t *h_letters, int len1, int len2, int radius, int size_cap, int classic,
                      int64_t max_nodes, int64_t *n_nodes_out, uint16_t *h_sizes, uint8_t *h_levels, int64_t cap_nodes,
                      uint32_t *h_edges, int64_t cap_edges, int64_t *n_edges_out);
+/* neibourhoods.cpp read_do_and_write (:58-103) for a whole input file at once: the radius-`radius` ball sizes of
+ * n_roots presentations in ONE exploration (every node carries the index of its start presentation and the
+ * visited set is keyed by (root, state), so the balls are independent but share every kernel launch).
+ * Root r = letters [h_off[2r], h_off[2r+1]) and [h_off[2r+1], h_off[2r+2]) of h_letters; h_counts[n_roots].
+ * max_nodes bounds the SUM of the ball sizes (ACS_ERR_NOMEM if exceeded: split the batch). */
+int acs_ball_sizes(int device, const int8_t *h_letters, const int64_t *h_off, int n_roots, int radius, int classic,
+                   int64_t max_nodes, int64_t *h_counts);
+
+/* ---- PPO update path: the non-GEMM part, fused --------------------------------------
+ * acs_gae replaces the generalised-advantage-estimation loop of ac_solver/agents/training.py:230-250:
+ * rewards / values / dones are [T, N] fp32 (time major, as the rollout stores them), next_value / next_done [N];
+ * advantages and returns [T, N] out.  Same fp32 operation order as the reference's elementwise torch ops
+ * (bit-identical results).  All pointers are device pointers; the work is enqueued on `stream`. */
+int acs_gae(const float *d_rewards, const float *d_values, const float *d_dones, const float *d_next_value,
+            const float *d_next_done, float *d_advantages, float *d_returns, int T, int64_t N, double gamma,
+            double gae_lambda, void *stream);
+/* acs_ppo_loss replaces the loss arithmetic of training.py:262-318 for one minibatch of B samples and ALSO
+ * returns its gradient: d_logits [B, n_actions] actor outputs, d_newvalue [B] critic outputs, d_action [B] int64,
+ * d_old_logprob / d_adv (raw advantages; normalised here when norm_adv) / d_returns / d_old_value [B].
+ * d_out8 = {loss, pg_loss, v_loss, entropy, approx_kl, clipfrac, 0, 0}; d_dlogits [B, n_actions] and d_dvalue [B] =
+ * d loss / d logits, d loss / d newvalue (feed them to the backward pass of the two networks).  loss_clip: the
+ * clipped surrogate, else the KL-penalised one with the device scalar *d_beta.  d_workspace: at least
+ * acs_ppo_loss_workspace_bytes() bytes of device memory. */
+int acs_ppo_loss_workspace_bytes(void);
+int acs_ppo_loss(const float *d_logits, const float *d_newvalue, const int64_t *d_action, const float *d_old_logprob,
+                 const float *d_adv, const float *d_returns, const float *d_old_value, const float *d_beta,
+                 float *d_dlogits, float *d_dvalue, float *d_out8, void *d_workspace, int64_t B, int n_actions,
+                 int norm_adv, int loss_clip, int clip_vloss, double clip_coef, double ent_coef, double vf_coef,
+                 void *stream);
 
 #ifdef __cplusplus
 }

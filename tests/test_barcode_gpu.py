@@ -84,3 +84,17 @@ def test_against_the_compiled_reference():
             subprocess.run([exe, src, dst, str(radius), str(int(classic))], check=True, stdout=subprocess.DEVNULL)
             expected = [int(x) for x in open(dst).read().split()]
             assert neighbourhood_sizes(pres, radius=radius, classic=classic) == expected
+
+
+def test_batched_balls_equal_single_runs(golden):
+    """Many balls in one exploration ((root, state) keys) == one exploration per presentation, also when a
+    batch outgrows its node store and is split, and when two roots are the same presentation."""
+    from ac_solver_b200.barcode import neighbourhood_size, neighbourhood_sizes
+
+    pres = [literal_eval(l) for l in golden["test_input"]] + [literal_eval(l) for l in golden["sample"][:4]]
+    pres = pres + [pres[1]]
+    single = [neighbourhood_size(p, radius=4) for p in pres]
+    assert neighbourhood_sizes(pres, radius=4) == single
+    assert neighbourhood_sizes(pres, radius=4, batch_roots=3) == single
+    assert neighbourhood_sizes(pres, radius=4, batch_bytes=40 << 20) == single  # forces NOMEM splits
+    assert neighbourhood_sizes(pres, radius=3, classic=True) == [neighbourhood_size(p, radius=3, classic=True) for p in pres]
