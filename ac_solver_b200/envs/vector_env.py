@@ -156,6 +156,8 @@ class ACVectorEnv:
         self.step_count.zero_()
         self.lens.copy_(self.initial_lens)
         self._normalized = bool(self.initial_normal_host.all())
+        if self._curriculum is not None:  # environment i is on pool state i again (the solved record is kept)
+            self._curriculum["cur_state"].copy_(self.torch.arange(self.num_envs, dtype=self.torch.int32, device=self.dev))
         return self.state.cpu().numpy(), {}
 
     def step(self, actions):

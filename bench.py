@@ -47,10 +47,12 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1 << 17)
     ap.add_argument("--skip-bfs", action="store_true")
     ap.add_argument("--bfs-budget", type=int, default=1_000_000_000, help="BASELINE.json configs[4]: 1e9 nodes")
-    ap.add_argument("--bfs-timeout", type=float, default=240.0)
+    ap.add_argument("--bfs-timeout", type=float, default=420.0)
     ap.add_argument("--skip-python-baseline", action="store_true")
     ap.add_argument("--skip-greedy", action="store_true")
     ap.add_argument("--skip-vecenv", action="store_true")
+    ap.add_argument("--skip-barcode", action="store_true")
+    ap.add_argument("--skip-ppo", action="store_true")
     ap.add_argument("--greedy-budget", type=int, default=1_000_000)
     return ap.parse_args()
 
@@ -494,6 +496,16 @@ def run_b200(args):
             line["vecenv"] = bench_vecenv(args)
         except Exception as e:
             line["vecenv"] = {"error": repr(e)}
+    if world == 1 and not args.skip_ppo:
+        try:
+            line["ppo"] = bench_ppo(args)
+        except Exception as e:
+            line["ppo"] = {"error": repr(e)}
+    if world == 1 and not args.skip_barcode:
+        try:
+            line["barcode"] = bench_barcode(args)
+        except Exception as e:
+            line["barcode"] = {"error": repr(e)}
     if not args.skip_greedy:
         try:
             greedy_line = bench_greedy(args, world, dist)
@@ -800,6 +812,109 @@ def bench_vecenv(args):
                                       "kind": "reference", "sample": "the reference's ACEnv.step, 64 envs x 200 steps, one core"}
     except Exception as e:
         out["cpu_baseline_python"] = {"unavailable": repr(e)}
+    return out
+
+
+def bench_ppo(args):
+    """the whole PPO iteration on the device at BASELINE.json configs[3]'s size (4096 environments,
+    horizon 200, the reference's 2x512 tanh actor and critic): rollout graph (policy, sampling, env step, reward
+    wrappers, curriculum) + acs_gae + graphed minibatch updates (fused loss/gradient kernel, clip, Adam).
+    Reported: training timesteps / s over whole updates, wall clock around ppo_training_loop after its warm-up."""
+    import torch
+
+    from ac_solver_b200.agents.args import parse_args as ppo_args
+    from ac_solver_b200.agents.environment import get_env
+    from ac_solver_b200.agents.ppo_agent import Agent
+    from ac_solver_b200.agents import training as T
+
+    n_envs, steps, updates = 4096, 200, 6
+    a = ppo_args(["--num-envs", str(n_envs), "--num-steps", str(steps), "--horizon-length", "200", "--nodes-counts", "512", "512",
+                  "--total-timesteps", str(n_envs * steps * updates), "--num-minibatches", "4", "--update-epochs", "1",
+                  "--norm-rewards", "--states-type", "all"])
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        a.num_envs = min(n_envs, 1190)  # get_env asserts num_envs <= number of distinct initial states (environment.py:80-83)
+        envs, initial_states, curr, rec, hist, processed = get_env(a)
+    # 4096 environments over the 1190-state pool: the vector env is rebuilt at full width on the same pool
+    from ac_solver_b200.envs.vector_env import ACVectorEnv
+
+    pool = np.stack(initial_states)
+    rows = pool[np.arange(n_envs) % len(pool)]
+    pool_x = np.concatenate([rows, pool])
+    envs = ACVectorEnv(rows, horizon_length=a.horizon_length, clip_rewards=(a.min_rew, a.max_rew), norm_rewards=True, gamma=a.gamma)
+    envs.enable_curriculum(pool_x, repeat_solved_prob=a.repeat_solved_prob, seed=a.seed)
+    a.num_envs, a.batch_size = n_envs, n_envs * steps
+    a.minibatch_size = a.batch_size // a.num_minibatches
+    dev = torch.device("cuda")
+    torch.manual_seed(0)
+    agent = Agent(envs, a.nodes_counts).to(dev)
+    opt = torch.optim.Adam(agent.parameters(), lr=torch.tensor(a.learning_rate, device=dev), eps=a.epsilon, capturable=True)
+    cwd = os.getcwd()
+    os.chdir("/tmp")
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            # first call: warm-up (graph capture, allocator); second call on the same objects is timed
+            a.total_timesteps = n_envs * steps * 2
+            T.ppo_training_loop(envs, a, dev, opt, agent, list(range(n_envs)), {"solved": set(), "unsolved": set()}, {}, set(),
+                                initial_states, checkpoint_every=0, progress=False)
+            a.total_timesteps = n_envs * steps * updates
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            log = T.ppo_training_loop(envs, a, dev, opt, agent, list(range(n_envs)), {"solved": set(), "unsolved": set()}, {},
+                                      set(), initial_states, checkpoint_every=0, progress=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+    finally:
+        os.chdir(cwd)
+    return {"metric": "PPO training timesteps/sec (rollout + GAE + update, whole iterations)",
+            "workload": f"{n_envs} envs x {steps} steps per update, {updates} updates, 2x512 tanh actor+critic fp32, 4 minibatches x 1 epoch, "
+                        "NormalizeReward + clip and curriculum on the device; the second ppo_training_loop call on warm objects "
+                        "(its own graph capture included)",
+            "timesteps_per_s": n_envs * steps * updates / dt, "seconds_per_update": dt / updates,
+            "value_loss": log["losses/value_loss"], "policy_loss": log["losses/policy_loss"], "entropy": log["losses/entropy_loss"],
+            "approx_kl": log["losses/approx_kl"], "episodes": log["charts/episode"],
+            "note": "the reference's loop steps 4096 Python environments one by one on the host: at its measured "
+                    "ACEnv.step rate (vecenv.cpu_baseline_python) the rollout alone is ~40 s per update"}
+
+
+def bench_barcode(args):
+    """radius-5 ball sizes of all 1190 Miller-Schupp presentations (the workload of
+    barcode_analysis/5_steps_neibourhoods) on the GPU, with a bounded sample through the reference's own C++ tool
+    (oracle/_ref/neibourhoods_ref, compiled from the reference's sources) timed and compared beside it."""
+    import subprocess
+    import tempfile
+    from ast import literal_eval
+
+    from ac_solver_b200.barcode import neighbourhood_sizes
+
+    data = os.path.join(ROOT, "ac_solver_b200", "search", "miller_schupp", "data", "all_presentations.txt")
+    lines = [l.strip() for l in open(data) if l.strip()]
+    pres = [literal_eval(l) for l in lines]
+    neighbourhood_sizes(pres[:2], radius=2)
+    t0 = time.perf_counter()
+    sizes = neighbourhood_sizes(pres, radius=5)
+    gpu_s = time.perf_counter() - t0
+    out = {"metric": "radius-5 neighbourhood sizes of the 1190 Miller-Schupp presentations (12 prime moves)",
+           "rows": len(pres), "states_total": int(sum(sizes)), "seconds": gpu_s, "states_per_s": sum(sizes) / gpu_s}
+    exe = os.path.join(ROOT, "oracle", "_ref", "neibourhoods_ref")
+    if os.path.exists(exe):
+        idx = list(range(0, len(lines), len(lines) // 12))[:12]
+        with tempfile.TemporaryDirectory() as d:
+            src, dst = os.path.join(d, "in.txt"), os.path.join(d, "out.txt")
+            with open(src, "w") as f:
+                f.write("\n".join(lines[i] for i in idx) + "\n")
+            t0 = time.perf_counter()
+            subprocess.run([exe, src, dst, "5", "0"], check=True, stdout=subprocess.DEVNULL)
+            ref_s = time.perf_counter() - t0
+            ref = [int(x) for x in open(dst).read().split()]
+        out["parity"] = {"rows_compared": len(idx), "mismatches": sum(1 for k, i in enumerate(idx) if ref[k] != sizes[i]),
+                         "checked": "ball sizes vs the reference's own C++ tool run here"}
+        out["cpu_baseline"] = {"value": sum(ref) / ref_s, "unit": "states/s", "cores": 1, "kind": "reference",
+                               "sample": f"oracle/_ref/neibourhoods_ref (the reference's neibourhoods.cpp compiled by oracle/Makefile) "
+                                         f"on {len(idx)} of the 1190 rows: {ref_s:.1f} s",
+                               "extrapolated_seconds_all_rows_1core": ref_s * sum(sizes) / max(sum(ref), 1)}
     return out
 
 
