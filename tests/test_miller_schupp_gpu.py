@@ -63,3 +63,22 @@ def test_trivialize_through_greedy_and_bfs(tmp_path, capsys):
     assert len(solved_b) == 1 and len(unsolved_b) == 7
     assert paths_b[0] == [(-1, 7), (1, 7), (7, 5), (0, 4), (5, 2)]
     assert "Applying bfs to presentations of n = 1, lenw = 1" in capsys.readouterr().out
+
+
+def test_bfs_solved_file_reproduced_on_the_gpu(miller_schupp):
+    """The reference's bfs_solved_presentations.txt (278 rows, settings not recorded upstream) is what
+    bfs(p, 1e6, cyclically_reduce_after_moves=True) solves: every one of the first 533 rows and a sample of
+    the rest through the GPU search."""
+    import contextlib
+    import io
+
+    from ac_solver_b200.search.breadth_first import bfs_device
+
+    listed = {int(k) for k in miller_schupp["bfs_solved_index"]}
+    assert len(listed) == 278 and max(listed) < 533
+    got = set()
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k in list(range(533)) + list(range(533, 1190, 13)):
+            if bfs_device(np.array(ms_row(miller_schupp, k), dtype=np.int8), 1_000_000, True)[0]:
+                got.add(k)
+    assert got == listed
