@@ -31,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 constexpr int kStreams = 3;
 constexpr int64_t kChunkRows = 1 << 17;  // rows per pipeline chunk of the *_host calls
+constexpr size_t kSmallCall = 64 * 1024;   // single-call API: everything goes through one pinned staging buffer
 
 struct Scratch {
     void* p = nullptr;
@@ -67,6 +68,7 @@ struct acs_ctx {
     Scratch scratch[kStreams];
     unsigned long long* d_err = nullptr;  // {count, min row}
     unsigned long long* h_err = nullptr;  // pinned: [0..1] reset values, [2..3] read-back
+    uint8_t* h_stage = nullptr;            // pinned staging of the small-call path of acs_generic_host (kSmallCall bytes)
     Scratch out;                           // acs_env_step_host: actions | reward | done | truncated of the whole call
     cudaEvent_t ev_start = nullptr, ev_done[kStreams] = {};
     std::mutex mu;  // the *_host calls share streams and scratch: one caller at a time per context
@@ -100,6 +102,7 @@ int acs_ctx_create(int device, acs_ctx** out) {
         e = cudaStreamCreateWithFlags(&c->streams[k], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(&c->d_err, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_err, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_stage, kSmallCall);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_start, cudaEventDisableTiming);
     for (int k = 0; k < kStreams && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming);
     if (e != cudaSuccess) {  // release whatever was created
@@ -126,6 +129,7 @@ void acs_ctx_destroy(acs_ctx* c) {
         if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
     if (c->d_err) cudaFree(c->d_err);
     if (c->h_err) cudaFreeHost(c->h_err);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     delete c;
 }
 
@@ -439,6 +443,35 @@ int acs_generic_host(acs_ctx* c, int op, const int8_t* h_in, const uint8_t* h_ac
     ACS_CUDA(cudaSetDevice(c->device));
     const size_t bytes = (size_t)n * width;
     const int aux_per_row = (op == ACS_OP_ACMOVE || op == ACS_OP_SIMPLIFY_PRESENTATION) ? 2 : 1;
+    {
+        // Small calls (the reference's one-presentation-at-a-time API: ACMove, ACEnv.step, simplify_*): the cost is
+        // API calls and latency, not bytes.  Layout [in | action | aux | out | status] in a pinned staging buffer and
+        // on the device: ONE upload of the prefix (aux arrives zeroed), the kernel, ONE download of the suffix.
+        const size_t s_act = align_up(bytes, 16), s_aux = s_act + align_up((size_t)n, 16);
+        const size_t s_out = s_aux + align_up((size_t)n * 4 * aux_per_row, 16), s_st = s_out + align_up(bytes, 16);
+        const size_t s_end = s_st + align_up((size_t)n, 16);
+        if (s_end <= kSmallCall) {
+            int rc = c->scratch[0].reserve(kSmallCall);
+            if (rc != ACS_OK) return rc;
+            uint8_t* d = static_cast<uint8_t*>(c->scratch[0].p);
+            uint8_t* h = c->h_stage;
+            cudaStream_t s = c->streams[0];
+            std::memcpy(h, h_in, bytes);
+            if (h_action) std::memcpy(h + s_act, h_action, (size_t)n);
+            std::memset(h + s_aux, 0, s_out - s_aux);
+            ACS_CUDA(cudaMemcpyAsync(d, h, s_out, cudaMemcpyHostToDevice, s));
+            rc = acs_generic_batch(op, reinterpret_cast<int8_t*>(d), h_action ? d + s_act : nullptr,
+                                   reinterpret_cast<int8_t*>(d + s_out), reinterpret_cast<int32_t*>(d + s_aux), d + s_st, n,
+                                   width, i, j, sign, cyclical, s);
+            if (rc != ACS_OK) return rc;
+            ACS_CUDA(cudaMemcpyAsync(h + s_aux, d + s_aux, s_end - s_aux, cudaMemcpyDeviceToHost, s));
+            ACS_CUDA(cudaStreamSynchronize(s));
+            std::memcpy(h_out, h + s_out, bytes);
+            std::memcpy(h_aux, h + s_aux, (size_t)n * 4 * aux_per_row);
+            std::memcpy(h_status, h + s_st, (size_t)n);
+            return ACS_OK;
+        }
+    }
     const size_t o_out = align_up(bytes, 256);
     const size_t o_act = o_out + align_up(bytes, 256);
     const size_t o_aux = o_act + align_up((size_t)n, 256);

@@ -232,6 +232,34 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run on (and first-touch the pinned buffers from) the host cores of the NUMA node the
+    GPU hangs off, so that the e2e copies of N ranks do not all land in one socket's memory.  Best effort: returns
+    what was done (or why not) for the JSON line."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"node": None, "why": "the platform reports no NUMA affinity for the GPU"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"node": node, "why": "none of the node's cores are in this process's affinity mask"}
+        os.sched_setaffinity(0, use)
+        return {"node": node, "cores": len(use), "gpu": bdf}
+    except Exception as e:  # sysfs layout, permissions: keep going unbound
+        return {"node": None, "why": repr(e)}
+
+
 def run_b200(args):
     import torch
 
@@ -243,6 +271,7 @@ def run_b200(args):
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -402,6 +431,23 @@ def run_b200(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    single = None
+    if rank == 0 and world == 1:
+        # the reference's one-presentation-at-a-time API through the GPU (latency, not throughput: H2D + kernel + D2H +
+        # stream sync per call); reported so that nobody mistakes the drop-in single calls for the fast path
+        from ac_solver_b200.envs.ac_moves import ACMove
+
+        p0 = host_states[0].copy()
+        ln = [int((p0[:mrl] != 0).sum()), int((p0[mrl:] != 0).sum())]
+        for k in range(50):
+            ACMove(k % 12, p0, mrl, ln)
+        t0 = time.perf_counter()
+        ncall = 2000
+        for k in range(ncall):
+            ACMove(k % 12, p0, mrl, ln)
+        single = {"ACMove_us_per_call": 1e6 * (time.perf_counter() - t0) / ncall, "calls": ncall,
+                  "note": "single-presentation ACMove(cyclical=True) through acs_generic_host; compare 1e6 / cpu_baseline_python.per_core"}
+
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         ms_per_step = ms / args.steps
@@ -443,6 +489,10 @@ def run_b200(args):
                            % (bool(FLAGS & 2), bool(FLAGS & 4))) if mrl == 36 else "acs::ac_step_*_kernel",
                 "kernel_flags": FLAGS,
                 "frac_of_nominal_8TBs": achieved / 8000.0,
+                # what the kernel really moves per move with the lengths carried (FLAGS & 4): the algorithmic 4*mrl+6 plus the
+                # step counter in and out (8), the two lengths in and out (4) and `truncated` (1)
+                "real_bytes_per_move": (4 * mrl + 6 + 13) if (FLAGS & 4) else (4 * mrl + 6 + 11),
+                "frac_real_traffic": achieved / peak * ((4 * mrl + 6 + 13) if (FLAGS & 4) else (4 * mrl + 6 + 11)) / (4 * mrl + 6),
             },
             "roofline_general": {
                 "bound": "hbm", "achieved": achieved_general, "peak": peak, "unit": "GB/s", "frac": achieved_general / peak,
@@ -459,10 +509,12 @@ def run_b200(args):
                 "d2h_bytes_per_step": rows * (rowb + 4 + 1 + 1),
                 "steps": e2e_steps,
                 "api": "acs_env_step_host: pinned host actions in; host observations, rewards, done, truncated out",
+                "numa_binding_rank0": numa,
                 "d2h_GBps_achieved": rows * (rowb + 6) * e2e_steps / e2e_s / 1e9,
                 "pinned_d2h_GBps_measured": d2h_gbps,
                 "frac_of_pinned_d2h": rows * (rowb + 6) * e2e_steps / e2e_s / 1e9 / d2h_gbps,
             },
+            "single_call": single,
             "gpu_launches": args.steps,  # kernels of the timed region (one ac_step kernel per step)
             "clocks": sampler.summary(),
         }
