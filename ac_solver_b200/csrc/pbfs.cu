@@ -792,13 +792,17 @@ __global__ void __launch_bounds__(256) pb_insert_kernel(const PbShard S) {
     uint32_t* bm = sh_bitmap(S, S.arena, st->buf);
     const uint64_t tmask = st->tmask;
     if (blockIdx.x == 0 && threadIdx.x == 0) st->records_recv += total;
-    // source by source (no per-record search for the source region); the grid offset rotates with the
-    // source so that the tail of one region and the head of the next keep all blocks busy
-    for (int src = 0; src < world; ++src) {
+    // Every block works on ONE source log (block b on source b mod G), so all G logs are walked at the same
+    // time and at the same pace: candidate ids grow along every log, hence the G walks touch the same moving
+    // window of the winner bitmap (here) and of the rank table (commit) -- it is read from HBM once per chunk,
+    // not once per source.  No per-record search for the source region either.
+    {
+    const int src = (int)(blockIdx.x % (unsigned)world);
+    const unsigned long long bsrc = blockIdx.x / (unsigned)world;
+    const unsigned long long nbsrc = (gridDim.x - (unsigned)src + (unsigned)world - 1u) / (unsigned)world;
     const unsigned long long n_src = R.vstart[src + 1] - R.vstart[src];
     const int64_t base_src = (int64_t)src * log_cap + (int64_t)R.cstart[src];
-    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_src;
-         v += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long v = bsrc * blockDim.x + threadIdx.x; v < n_src; v += nbsrc * blockDim.x) {
         const int64_t i = base_src + (int64_t)v;
         const Key<W> key = load_key_cg<W>(in_keys, (uint64_t)i);
         const uint32_t c = __ldcg(in_c + i);
@@ -1179,11 +1183,13 @@ __global__ void __launch_bounds__(256) pb_commit_kernel(const PbShard S) {
     const uint64_t n_nodes0 = (uint64_t)st->n_nodes0, n_local0 = (uint64_t)st->n_local0;
     const uint64_t head0 = (uint64_t)st->head0;
     (void)total;
-    for (int src = 0; src < S.world; ++src) {  // source by source: no per-record search for the source region
+    {  // block b walks source log b mod G (see pb_insert_kernel): the rank table is streamed once per chunk
+    const int src = (int)(blockIdx.x % (unsigned)S.world);
+    const unsigned long long bsrc = blockIdx.x / (unsigned)S.world;
+    const unsigned long long nbsrc = (gridDim.x - (unsigned)src + (unsigned)S.world - 1u) / (unsigned)S.world;
     const unsigned long long n_src = R.vstart[src + 1] - R.vstart[src];
     const int64_t base_src = (int64_t)src * log_cap + (int64_t)R.cstart[src];
-    for (unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_src;
-         v += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long v = bsrc * blockDim.x + threadIdx.x; v < n_src; v += nbsrc * blockDim.x) {
         const int64_t i = base_src + (int64_t)v;
         const uint64_t c = __ldcg(in_c + i);
         if (c >= limit) continue;
@@ -1491,8 +1497,9 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ib, pb_insert_kernel<2>, 256, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cb, pb_commit_kernel<2>, 256, 0);
     }
-    b->insert_blocks = b->sms * std::max(ib, 1);
-    b->commit_blocks = b->sms * std::max(cb, 1);
+    // (at least one block per source log: block b works on source b mod world)
+    b->insert_blocks = std::max(b->sms * std::max(ib, 1), world);
+    b->commit_blocks = std::max(b->sms * std::max(cb, 1), world);
     for (int r = 0; r < kPbMaxWorld; ++r) S.peer[r] = nullptr;
     S.peer[rank] = S.arena;
     b->connected = world == 1;

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--ref-rows", type=int, default=64)
     ap.add_argument("--radius", type=int, default=5)
     ap.add_argument("--classic", action="store_true")
+    ap.add_argument("--simplex", type=int, default=0, help="also time the simplex dump of ac_bfs.cpp for this n")
     args = ap.parse_args()
     from ac_solver_b200.barcode import neighbourhood_sizes
 
@@ -54,6 +55,29 @@ def main():
                                   "extrapolated_seconds_all_rows": ref_s * sum(sizes) / max(ref_states, 1)},
                     "parity": {"rows_compared": len(idx), "mismatches": mism},
                     "speedup_vs_reference_1core": (sum(sizes) / gpu_s) / (ref_states / ref_s)})
+    if args.simplex:
+        import hashlib
+
+        from ac_solver_b200.barcode import write_simplex_files
+
+        n = args.simplex
+        names = ("zero_simplices", "zero_filtrations", "one_simplices", "one_filtrations")
+        with tempfile.TemporaryDirectory() as d:
+            write_simplex_files(4, d, classic=args.classic)  # warm-up
+            t0 = time.perf_counter()
+            data = write_simplex_files(n, d, classic=args.classic)
+            gpu_s = time.perf_counter() - t0
+            mine = [hashlib.sha256(open(os.path.join(d, f"{x}_{n}"), "rb").read()).hexdigest() for x in names]
+        sx = {"n": n, "vertices": int(data["n_vertices"]), "edges": int(len(data["one_filt"])), "gpu_seconds_incl_file_writes": gpu_s}
+        ref_exe = os.path.join(ROOT, "oracle", "_ref", "ac_bfs_classic" if args.classic else "ac_bfs_prime")
+        if os.path.exists(ref_exe):
+            with tempfile.TemporaryDirectory() as d:
+                t0 = time.perf_counter()
+                subprocess.run([ref_exe, str(n)], cwd=d, check=True, stdout=subprocess.DEVNULL)
+                sx["reference_seconds"] = time.perf_counter() - t0
+                ref = [hashlib.sha256(open(os.path.join(d, f"{x}_{n}"), "rb").read()).hexdigest() for x in names]
+            sx["files_byte_identical"] = mine == ref
+        out["simplex"] = sx
     print(json.dumps(out))
 
 
