@@ -612,7 +612,7 @@ __device__ __forceinline__ void pb_flush_cta(const PbShard& S, const DestBase* D
 }
 
 template <int W, bool TRUSTED>
-__global__ void __launch_bounds__(256) pb_expand_cta_kernel(const PbShard S) {
+__global__ void __launch_bounds__(512) pb_expand_cta_kernel(const PbShard S) {
     const PbState* st = S.st;
     if (st->done) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -1474,7 +1474,11 @@ int acs_pbfs_create(int device, int rank, int world, int mrl, int64_t max_nodes,
     {
         const char* e2 = std::getenv("ACS_PBFS_CTA_STAGE");
         b->cta_stage = world > 1 && !(e2 && e2[0] == '0');
-        b->cta_threads = 256;
+        b->cta_threads = 512;  // 16 warps stage together: ~120 records (1.9 KB of keys) per destination and flush at G = 8
+        if (const char* e3 = std::getenv("ACS_PBFS_CTA_THREADS")) {
+            const int v = std::atoi(e3);
+            if (v == 128 || v == 256 || v == 512) b->cta_threads = v;
+        }
         b->cta_smem = b->W == 1 ? cta_stage_bytes<1>(b->cta_threads / 32) : cta_stage_bytes<2>(b->cta_threads / 32);
         int cps = 1;
         if (b->W == 1) {

@@ -214,8 +214,14 @@ class ACVectorEnv:
             if not self.initial_normal_host[fin_host].all():
                 self._normalized = False  # a non-normal initial state: next step re-simplifies
         if as_numpy:
-            return (obs.cpu().numpy(), reward.cpu().numpy(), self.done.cpu().numpy().astype(bool),
-                    self.truncated.cpu().numpy().astype(bool), infos)
+            # one device-to-host copy for the four outputs: [obs | reward f64 | done | truncated] as bytes
+            n, w = self.num_envs, self.state.shape[1]
+            packed = t.cat([obs.reshape(-1).view(t.uint8), reward.contiguous().view(t.uint8), self.done, self.truncated]).cpu().numpy()
+            o = packed[: n * w].view(np.int8).reshape(n, w).copy()
+            r = packed[n * w : n * w + 8 * n].view(np.float64).copy()
+            d = packed[n * w + 8 * n : n * w + 9 * n].astype(bool)
+            tr = packed[n * w + 9 * n :].astype(bool)
+            return o, r, d, tr, infos
         return obs.clone(), reward, self.done.bool(), self.truncated.bool(), infos
 
     # ---------------------------------------------------------------------------------------
