@@ -579,6 +579,9 @@ int greedy_run_impl(acs_greedy* g, const int8_t* h_pres, int32_t* h_paths, acs_s
         auto smem_for = [](int buckets) { return ((sizeof(GbShared) + 15) / 16) * 16 + (size_t)buckets * sizeof(GbBucket); };
         GR_CUDA(cudaFuncSetAttribute(greedy_bucket_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem_for(kGbBuckets2)));
+        // several CTAs per SM in pass 1: ask for the largest shared-memory carve-out
+        GR_CUDA(cudaFuncSetAttribute(greedy_bucket_kernel<W>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
         const bool debug = std::getenv("ACS_GREEDY_DEBUG") != nullptr;
         for (int pass = 0; pass < 2; ++pass) {
             g->gb.max_buckets = pass == 0 ? kGbBuckets1 : kGbBuckets2;

@@ -144,7 +144,11 @@ __device__ __forceinline__ int gb_find(const GbBucket* B, int nb, uint32_t key) 
 }
 
 template <int W>
-__global__ void __launch_bounds__(kGbThreads) greedy_bucket_kernel(const GreedyArgs A, const GbArgs X) {
+#ifndef GB_MIN_BLOCKS
+#define GB_MIN_BLOCKS 5  // resident CTAs per SM the register allocation must allow: 48 registers, 5 x 42 KB of shared memory
+                         // -> 740 searches in flight on 148 SMs (the 657 unsolved rows of config 3 run as one wave)
+#endif
+__global__ void __launch_bounds__(kGbThreads, GB_MIN_BLOCKS) greedy_bucket_kernel(const GreedyArgs A, const GbArgs X) {
     extern __shared__ __align__(16) unsigned char gb_smem_raw[];
     GbShared& sh = *reinterpret_cast<GbShared*>(gb_smem_raw);
     GbBucket* B = reinterpret_cast<GbBucket*>(gb_smem_raw + ((sizeof(GbShared) + 15) / 16) * 16);
