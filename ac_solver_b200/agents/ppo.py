@@ -1,7 +1,11 @@
-"""Entry point of PPO training on the GPU-resident AC environment (reference: ``ac_solver/agents/ppo.py``):
+"""PPO training on the GPU-resident AC environment -- the command-line entry point.
 
-    python -m ac_solver_b200.agents.ppo [--num-envs 4096 --num-steps 200 ...]      # flags: agents/args.py
-"""
+    python -m ac_solver_b200.agents.ppo --num-envs 4096 --num-steps 200 --nodes-counts 512 512
+
+Flags are the reference's (agents/args.py mirrors ``ac_solver/agents/args.py``).  Differences from the
+reference's ``ac_solver/agents/ppo.py``: a CUDA device is mandatory (the environments live on it), the
+optimiser is a capturable Adam whose learning rate is a device scalar (the minibatch step is replayed
+as a CUDA graph), and the trained bookkeeping is returned to the caller."""
 
 from __future__ import annotations
 
@@ -9,32 +13,39 @@ import random
 
 import numpy as np
 import torch
-from torch.optim import Adam
 
-from .args import parse_args
-from .environment import get_env
-from .ppo_agent import Agent
-from .training import ppo_training_loop
+from . import args as _args
+from . import environment, ppo_agent, training
+
+
+def seed_everything(seed, deterministic=True):
+    for fn in (random.seed, np.random.seed, torch.manual_seed):
+        fn(seed)
+    torch.backends.cudnn.deterministic = bool(deterministic)
+
+
+def make_optimizer(agent, learning_rate, eps, device):
+    lr = torch.tensor(float(learning_rate), device=device)  # device-resident: annealed with fill_() between graph replays
+    return torch.optim.Adam(agent.parameters(), lr=lr, eps=eps, capturable=True)
 
 
 def train_ppo(argv=None):
-    args = parse_args(argv)
-    random.seed(args.seed)
-    np.random.seed(args.seed)
-    torch.manual_seed(args.seed)
-    torch.backends.cudnn.deterministic = args.torch_deterministic
-    if not (torch.cuda.is_available() and args.cuda):
+    """Parse the flags, build environments / agent / optimiser and run ``ppo_training_loop``.
+    Returns ``(last_log, success_record, ACMoves_hist)``."""
+    cfg = _args.parse_args(argv)
+    seed_everything(cfg.seed, cfg.torch_deterministic)
+    if not (cfg.cuda and torch.cuda.is_available()):
         raise RuntimeError("ac_solver_b200 trains on a CUDA device only: the environment lives on the GPU")
     device = torch.device("cuda")
-    envs, initial_states, curr_states, success_record, ACMoves_hist, states_processed = get_env(args)
-    agent = Agent(envs, args.nodes_counts).to(device)
-    # capturable Adam with a device-resident learning rate: the whole minibatch step is one CUDA graph
-    optimizer = Adam(agent.parameters(), lr=torch.tensor(args.learning_rate, device=device), eps=args.epsilon,
-                     capturable=True)
-    log = ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success_record, ACMoves_hist,
-                            states_processed, initial_states)
-    envs.close()
-    return log, success_record, ACMoves_hist
+    envs, initial_states, curr_states, success_record, moves_hist, processed = environment.get_env(cfg)
+    try:
+        agent = ppo_agent.Agent(envs, cfg.nodes_counts).to(device)
+        optimizer = make_optimizer(agent, cfg.learning_rate, cfg.epsilon, device)
+        log = training.ppo_training_loop(envs, cfg, device, optimizer, agent, curr_states, success_record, moves_hist,
+                                         processed, initial_states)
+    finally:
+        envs.close()
+    return log, success_record, moves_hist
 
 
 if __name__ == "__main__":
