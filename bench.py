@@ -244,7 +244,20 @@ def bind_to_gpu_numa_node(local_rank):
         with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
-            return {"node": None, "why": "the platform reports no NUMA affinity for the GPU"}
+            # sysfs knows nothing (containers often hide it): ask NVML for the GPU's ideal CPU set
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bdf.encode() if hasattr(bdf, "encode") else bdf)
+            ncpu = os.cpu_count() or 1
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            use = cpus & allowed
+            if not use or use == allowed:
+                return {"node": None, "why": "neither sysfs nor NVML reports a CPU affinity narrower than this process's mask"}
+            os.sched_setaffinity(0, use)
+            return {"node": "nvml", "cores": len(use), "gpu": bdf}
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
             for part in f.read().strip().split(","):

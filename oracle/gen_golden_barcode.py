@@ -45,7 +45,12 @@ def main():
     solved = [l.strip() for l in open(os.path.join(REF, "5_steps_neibourhoods", "solved_miller_schupp_presentations.txt")) if l.strip()]
     unsolved = [l.strip() for l in open(os.path.join(REF, "5_steps_neibourhoods", "unsolved_miller_schupp_presentations.txt")) if l.strip()]
     sample = solved[:: max(1, len(solved) // 10)][:10] + unsolved[:: max(1, len(unsolved) // 10)][:10]
-    g = {"test_input": test_input, "test_input_prime_r5": ball_sizes(test_input, 5, False),
+    # edge cases of the input format (neibourhoods.cpp:80-90 drops the zeros of each half): an empty relator, two equal
+    # relators, a relator and its inverse, a NON-reduced start word, the empty presentation
+    edge = ["[0, 0, 0, 0, 2, 0, 0, 0]", "[1, 2, 0, 0, 1, 2, 0, 0]", "[1, 2, 0, 0, -2, -1, 0, 0]", "[1, -1, 0, 0, 2, 0, 0, 0]",
+            "[0, 0, 0, 0]"]
+    g = {"edge": edge, "edge_prime_r3": ball_sizes(edge, 3, False), "edge_classic_r3": ball_sizes(edge, 3, True),
+         "test_input": test_input, "test_input_prime_r5": ball_sizes(test_input, 5, False),
          "test_input_classic_r5": ball_sizes(test_input, 5, True), "test_input_prime_r3": ball_sizes(test_input, 3, False),
          "sample": sample, "sample_prime_r5": ball_sizes(sample, 5, False), "sample_classic_r4": ball_sizes(sample, 4, True),
          "simplex": {f"{'classic' if c else 'prime'}_{n}": simplex(n, c) for c in (False, True) for n in (4, 7, 10)}}

@@ -98,3 +98,14 @@ def test_batched_balls_equal_single_runs(golden):
     assert neighbourhood_sizes(pres, radius=4, batch_roots=3) == single
     assert neighbourhood_sizes(pres, radius=4, batch_bytes=40 << 20) == single  # forces NOMEM splits
     assert neighbourhood_sizes(pres, radius=3, classic=True) == [neighbourhood_size(p, radius=3, classic=True) for p in pres]
+
+
+def test_edge_case_inputs(golden):
+    """Empty relator, equal relators, a relator and its inverse, a non-reduced start word, the empty presentation:
+    same ball sizes as the reference's tool (golden), batched and one by one."""
+    from ac_solver_b200.barcode import neighbourhood_size, neighbourhood_sizes
+
+    pres = [literal_eval(l) for l in golden["edge"]]
+    assert neighbourhood_sizes(pres, radius=3) == golden["edge_prime_r3"]
+    assert neighbourhood_sizes(pres, radius=3, classic=True) == golden["edge_classic_r3"]
+    assert [neighbourhood_size(p, radius=3) for p in pres] == golden["edge_prime_r3"]
