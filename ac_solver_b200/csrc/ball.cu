@@ -49,6 +49,7 @@ struct BallArgs {
     uint64_t lo;        // first parent of the chunk
     uint64_t nparents, n_nodes;
     int L, K, classic, size_cap, want_edges;
+    int literal;        // some start word is not freely reduced: restate the reference's reduce_ pass by pass (see ball_move)
 };
 
 __device__ __forceinline__ bool rel_less(const int8_t* x, int lx, const int8_t* y, int ly) {
@@ -73,10 +74,44 @@ __device__ __forceinline__ int push_reduced(int8_t* out, int n, int8_t v) {
     out[n] = v;
     return n + 1;
 }
+// The reference's reduce0_ (AC_UTILS_no_hash.cpp:58-79), literally: one left-to-right pass that drops adjacent
+// inverse pairs, and keeps the last letter iff it does not cancel against its LEFT NEIGHBOUR IN THE INPUT -- also
+// when that neighbour was already consumed by a pair (so [.., X, x, X] loses its last letter although free
+// reduction keeps it).  reduce_ (:81-88) repeats the pass until nothing changes.  On a concatenation / conjugation
+// of freely reduced words the fixpoint IS the free reduction (the odd case needs x X x at the end of the input),
+// so the fast path below uses a stack; only runs that start from a non-reduced word take this literal path.
+__device__ int reduce_literal(int8_t* w, int n, int8_t* tmp) {
+    int8_t* cur = w;
+    int8_t* nxt = tmp;
+    for (;;) {
+        int m = 0;
+        if (n < 2) {
+            m = n;
+            if (n == 1) nxt[0] = cur[0];
+        } else {
+            int j = 0;
+            while (j < n - 1) {
+                if (cur[j] + cur[j + 1] == 0) j += 2;
+                else nxt[m++] = cur[j++];
+            }
+            if (cur[n - 1] + cur[n - 2] != 0) nxt[m++] = cur[n - 1];
+        }
+        int8_t* t = cur;
+        cur = nxt;
+        nxt = t;
+        if (m == n) break;  // a pass that removes nothing returns its input
+        n = m;
+    }
+    if (cur != w)
+        for (int i = 0; i < n; ++i) w[i] = cur[i];
+    return n;
+}
 
 // child of (r1, r2) under move t (AC_UTILS_no_hash.cpp:153-211, AC_UTILS_as_sets.h:337-362); the
-// changed relator is built fully reduced in `nw` (capacity 2L+2); returns its length, `which` = 0/1
-__device__ int ball_move(const int8_t* r1, int l1, const int8_t* r2, int l2, int t, bool classic, int8_t* nw, int& which) {
+// changed relator is built fully reduced in `nw` (capacity 2L+2); returns its length, `which` = 0/1.
+// literal: build the raw word and reduce it with the reference's own pass structure (tmp: second buffer).
+__device__ int ball_move(const int8_t* r1, int l1, const int8_t* r2, int l2, int t, bool classic, int8_t* nw, int& which,
+                         bool literal, int8_t* tmp) {
     // decode: op 0 = concat(x, y), 1 = concat(x, inv y), 2 = conj(x, g), 3 = inv(x)
     int op, tgt, g = 0;
     bool other_first = false;  // concat(other, target) instead of concat(target, other)
@@ -113,6 +148,28 @@ __device__ int ball_move(const int8_t* r1, int l1, const int8_t* r2, int l2, int
     const int8_t* y = tgt ? r1 : r2;
     const int ly = tgt ? l1 : l2;
     int n = 0;
+    if (literal) {
+        // raw words exactly as concat_ / conj0_ / inv0_ assemble them; inv0_ alone does not reduce (:104-110)
+        if (op == 0) {
+            const int8_t* p = other_first ? y : x;
+            const int lp = other_first ? ly : lx;
+            const int8_t* q = other_first ? x : y;
+            const int lq = other_first ? lx : ly;
+            for (int i = 0; i < lp; ++i) nw[n++] = p[i];
+            for (int i = 0; i < lq; ++i) nw[n++] = q[i];
+        } else if (op == 1) {
+            for (int i = 0; i < lx; ++i) nw[n++] = x[i];
+            for (int i = ly - 1; i >= 0; --i) nw[n++] = (int8_t)-y[i];
+        } else if (op == 2) {
+            nw[n++] = (int8_t)-g;
+            for (int i = 0; i < lx; ++i) nw[n++] = x[i];
+            nw[n++] = (int8_t)g;
+        } else {
+            for (int i = lx - 1; i >= 0; --i) nw[n++] = (int8_t)-x[i];
+            return n;
+        }
+        return reduce_literal(nw, n, tmp);
+    }
     if (op == 0) {
         if (other_first) {
             for (int i = 0; i < ly; ++i) n = push_reduced(nw, n, y[i]);
@@ -145,8 +202,9 @@ __global__ void __launch_bounds__(kBallThreads) ball_expand_kernel(const BallArg
     const int8_t* r2 = r1 + L;
     const int l1 = A.lens[2 * p], l2 = A.lens[2 * p + 1];
     int8_t nw[1026];  // local memory; L <= 512
+    int8_t tmp[1026];  // second buffer of the literal reduction (untouched on the fast path)
     int which;
-    const int n = ball_move(r1, l1, r2, l2, t, A.classic != 0, nw, which);
+    const int n = ball_move(r1, l1, r2, l2, t, A.classic != 0, nw, which, A.literal != 0, tmp);
     uint16_t o1 = 0xFFFF, o2 = 0xFFFF;
     if (n > L) {
         // with a size cap the stride IS the cap: such a child is simply too long (ac_bfs.cpp:60); without one
@@ -398,6 +456,10 @@ int ball_run(int device, const int8_t* h_letters, const int64_t* off, int n_root
     }
     for (int64_t i = 0; i < off[2 * n_roots]; ++i)
         if (h_letters[i] == 0 || h_letters[i] < -2 || h_letters[i] > 2) return ball_fail(ACS_ERR_INVALID, "ball: letters must be +-1, +-2");
+    bool literal = false;  // a start word with an adjacent inverse pair: the whole run follows the reference's reduce_ literally
+    for (int k = 0; k < 2 * n_roots && !literal; ++k)
+        for (int64_t i = off[k]; i + 1 < off[k + 1]; ++i)
+            if (h_letters[i] + h_letters[i + 1] == 0) literal = true;
     const int K = classic ? 14 : 12;
     // stride: a relator at most doubles per move (concatenation); radius-bounded runs size it from the start
     int L = size_cap > 0 ? size_cap : max_len;
@@ -456,6 +518,7 @@ int ball_run(int device, const int8_t* h_letters, const int64_t* off, int n_root
     A.classic = classic ? 1 : 0;
     A.size_cap = size_cap;
     A.want_edges = want_edges ? 1 : 0;
+    A.literal = literal ? 1 : 0;
     BALL_CUDA(cudaMemset(A.table, 0, tcap * 8));
     BALL_CUDA(cudaMemset(A.ctrl, 0, 32));
     // roots: the sorted pairs (sort_, AC_UTILS_no_hash.cpp:131-147) as nodes 0 .. n_roots-1, level 0

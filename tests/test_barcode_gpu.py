@@ -76,6 +76,14 @@ def test_against_the_compiled_reference():
                     w.append(c)
             rows.append(w + [0] * (8 - len(w)))
         pres.append(rows[0] + rows[1])
+    # ... and words that are NOT freely reduced: the reference's reduce_ is not plain free reduction on them
+    # (AC_UTILS_no_hash.cpp:58-88), and inv0_ does not reduce at all -- the engine restates both literally
+    for _ in range(6):
+        rows = []
+        for _h in range(2):
+            w = [int(rng.choice([-2, -1, 1, 2])) for _ in range(int(rng.integers(0, 7)))]
+            rows.append(w + [0] * (8 - len(w)))
+        pres.append(rows[0] + rows[1])
     with tempfile.TemporaryDirectory() as d:
         src, dst = os.path.join(d, "in.txt"), os.path.join(d, "out.txt")
         with open(src, "w") as f:
