@@ -561,6 +561,11 @@ def run_b200(args):
             line["vecenv"] = bench_vecenv(args)
         except Exception as e:
             line["vecenv"] = {"error": repr(e)}
+    if world == 1:
+        try:
+            line["config1"] = bench_config1()
+        except Exception as e:
+            line["config1"] = {"error": repr(e)}
     if world == 1 and not args.skip_ppo:
         try:
             line["ppo"] = bench_ppo(args)
@@ -839,12 +844,37 @@ def bench_vecenv(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     env.check_errors()
+    # the environment side alone (no policy): actions drawn on the device, same step / reward wrappers / curriculum
+    def env_only_step():
+        env.step_device(torch.randint(0, 12, (n_envs,), device=env.dev, dtype=torch.uint8))
+        return env.transformed_reward()
+
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            env_only_step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph2):
+        env_only_step()
+    for _ in range(20):
+        graph2.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(replays):
+        graph2.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_env = e0.elapsed_time(e1)
+    env.check_errors()
     c = env.curriculum_counters()
     out = {
         "metric": "PPO rollout env steps/sec (env side)", "workload": "BASELINE.json configs[3]: 4096 envs, horizon 200, "
         "torch 2x512 actor on device, device-side NormalizeReward+clip and curriculum reset, one CUDA graph per vector step",
         "env_steps_per_s": n_envs * replays / (ms * 1e-3), "us_per_vector_step": 1e3 * ms / replays,
         "episodes_finished": c["episodes"], "states_solved": c["n_solved"], "host_syncs_per_step": 0,
+        "env_only_steps_per_s": n_envs * replays / (ms_env * 1e-3), "env_only_us_per_vector_step": 1e3 * ms_env / replays,
+        "env_only_note": "same graph without the actor: random actions drawn on the device; the policy GEMMs (fp32, cuBLAS) are the rest",
     }
     from oracle import oracle as O
 
@@ -877,6 +907,50 @@ def bench_vecenv(args):
                                       "kind": "reference", "sample": "the reference's ACEnv.step, 64 envs x 200 steps, one core"}
     except Exception as e:
         out["cpu_baseline_python"] = {"unavailable": repr(e)}
+    return out
+
+
+def bench_config1():
+    """BASELINE.json configs[0]: bfs() on the README presentation AK(2), default budget 10 000 -- the reference's own
+    CPU-runnable case.  Value is parity (result, visited count; the visited array is pinned by the tests), the wall time
+    of the drop-in call is reported beside the reference's own bfs() (pure Python, staged under baseline/_ref) and the C
+    oracle."""
+    import contextlib
+    import io
+
+    from ac_solver_b200 import bfs
+    from ac_solver_b200.search.breadth_first import bfs_device
+    from oracle import oracle as O
+
+    ak2 = np.array([1, 1, -2, -2, -2, 0, 0, 1, 2, 1, -2, -1, -2, 0])
+    with contextlib.redirect_stdout(io.StringIO()):
+        bfs(ak2)  # warm-up
+        t0 = time.perf_counter()
+        reps = 20
+        for _ in range(reps):
+            res = bfs(ak2)
+        gpu_s = (time.perf_counter() - t0) / reps
+        _, _, info = bfs_device(ak2.astype(np.int8), 10000)
+    t0 = time.perf_counter()
+    es, ep, ei = O.bfs(ak2, 10000)
+    port_s = time.perf_counter() - t0
+    out = {"workload": "bfs([1,1,-2,-2,-2,0,0,1,2,1,-2,-1,-2,0]) with the default max_nodes_to_explore=10000",
+           "result": [bool(res[0]), res[1]], "visited": int(info["n_visited"]), "expanded": int(info["n_expanded"]),
+           "parity": {"result_equals_oracle": (bool(res[0]), res[1]) == (bool(es), ep), "visited_equals_oracle": int(info["n_visited"]) == int(ei["n_visited"]),
+                      "expected": "(False, None), 10002 visited (SURVEY 8d)"},
+           "seconds_per_call": gpu_s, "c_port_seconds": port_s}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        from ac_solver.search.breadth_first import bfs as ref_bfs
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            t0 = time.perf_counter()
+            rr = ref_bfs(ak2.copy(), max_nodes_to_explore=10000)
+            out["reference_python_seconds"] = time.perf_counter() - t0
+        out["parity"]["result_equals_reference_python"] = (bool(rr[0]), rr[1]) == (bool(res[0]), res[1])
+    except Exception as e:
+        out["reference_python_seconds"] = None
+        out["reference_python_error"] = repr(e)
     return out
 
 
