@@ -442,6 +442,7 @@ int ball_run(int device, const int8_t* h_letters, const int64_t* off, int n_root
              int64_t max_nodes, int64_t* n_nodes_out, int64_t* h_counts, uint16_t* h_sizes, uint8_t* h_levels,
              int64_t cap_nodes, uint32_t* h_edges, int64_t cap_edges, int64_t* n_edges_out) {
     if (!h_letters || !off || n_roots < 1 || max_nodes < n_roots) return ball_fail(ACS_ERR_INVALID, "ball: bad argument");
+    if (max_nodes > (int64_t)3500000000ll) return ball_fail(ACS_ERR_UNSUPPORTED, "ball: node indices are 32-bit (max_nodes <= 3.5e9)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();

@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossParams
         for (int k = 0; k < MAXA; ++k) se += k < P.A ? __expf(z[k] - zmax) : 0.f;
         const float lse = zmax + __logf(se);
         const int a = (int)P.action[i];
-        float H = 0.f, logp_a = 0.f;
+        // an action outside [0, A) has no log-probability (torch's Categorical.log_prob raises): poison the row
+        float H = 0.f, logp_a = (a >= 0 && a < P.A) ? 0.f : __int_as_float(0x7fc00000);
         float p[MAXA];
 #pragma unroll
         for (int k = 0; k < MAXA; ++k) {
