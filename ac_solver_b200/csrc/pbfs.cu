@@ -263,6 +263,27 @@ __global__ void __launch_bounds__(256) pb_prep_kernel(const PbShard S) {
     }
 }
 
+// Moves that need not be generated from a node, given the link (parent gid << 4 | action) that created it: their
+// children are certainly duplicates of candidates with a SMALLER id, so they can never win a slot, start a new
+// minimal length, be the first solved child or move the budget cut -- skipping them changes nothing observable.
+//  * back edge (searches without cyclic reduction): the move that undoes the creating move leads to the parent.
+//    Inverse pairs: r1<-r1 r0 / r1<-r1 r0^-1 (0,2); r0<-r0 r1^-1 / r0<-r0 r1 (1,3); conjugation by g / g^-1.
+//  * commuting conjugations: ids 4..11 conjugate r0 (odd ids) or r1 (even ids), and the two act on different
+//    relators independently (length cap, free / cyclic reduction are per relator).  For B = S.m' and a conjugation
+//    m < m' of the OTHER relator, B.m = (S.m).m'; the state S.m was discovered no later than S's expansion with an
+//    id below B's, so it is expanded before B and generates the same child under a smaller candidate id.
+// Not for children of the root: a caller-supplied root need not be a normal form, and its children are the first
+// fully simplified states.
+template <bool TRUSTED>
+__device__ __forceinline__ uint32_t skip_moves(int64_t pl, bool cyc) {
+    if (!TRUSTED || pl < 16) return 0u;
+    const int mp = (int)(pl & 15);
+    uint32_t skip = 0;
+    if (!cyc) skip |= 1u << ((0x7654BA981032ull >> (4 * mp)) & 15);
+    if (mp >= 4) skip |= ((mp & 1) ? 0x550u : 0xAA0u) & ((1u << mp) - 1u);
+    return skip;
+}
+
 // ---- expand ----------------------------------------------------------------------------------
 // Per-warp staging in shared memory: kStage records (key, candidate id, destination rank) in
 // generation order, a second buffer of the same size for the destination-sorted copy, and the
@@ -439,17 +460,12 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
 #pragma unroll
         for (int i = 0; i < 2 * W; ++i) pk.k[i] = 0;
         uint64_t pg = 0;
-        int back = -1;  // the move that undoes the one which created this node: its child is the node's own parent
+        uint32_t skip = 0;  // moves of this node whose child is certainly a duplicate of an EARLIER candidate
         if (valid) {
             int64_t pl, gj;
             node_load<W>(S.nodes, (uint64_t)j, pk, pl, gj);
             pg = (uint64_t)gj;
-            if (TRUSTED && !cyc) {
-                // inverse pairs: r1<-r1 r0 / r1<-r1 r0^-1 (0,2); r0<-r0 r1^-1 / r0<-r0 r1 (1,3); conjugation by g / g^-1
-                // (not for children of the root: a caller-supplied root need not be a normal form, and
-                // then the inverse move leads to its simplified form, a different state)
-                if (pl >= 16) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
-            }
+            skip = skip_moves<TRUSTED>(pl, cyc);
         }
         Rel<2 * W> p0, p1;
         split_key<W>(pk, p0, p1);
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(256) pb_expand_kernel(const PbShard S, int war
             Key<W> child;
 #pragma unroll
             for (int i = 0; i < 2 * W; ++i) child.k[i] = 0;
-            if (valid && a != back) {
+            if (valid && !((skip >> a) & 1u)) {
                 bool co;
                 const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
                 if (stt != ST_OK) {
@@ -642,14 +658,12 @@ __global__ void __launch_bounds__(512) pb_expand_cta_kernel(const PbShard S) {
 #pragma unroll
         for (int i = 0; i < 2 * W; ++i) pk.k[i] = 0;
         uint64_t pg = 0;
-        int back = -1;  // see pb_expand_kernel
+        uint32_t skip = 0;  // see skip_moves
         if (valid) {
             int64_t pl, gj;
             node_load<W>(S.nodes, (uint64_t)j, pk, pl, gj);
             pg = (uint64_t)gj;
-            if (TRUSTED && !cyc) {
-                if (pl >= 16) back = (int)((0x7654BA981032ull >> (4 * (pl & 15))) & 15);
-            }
+            skip = skip_moves<TRUSTED>(pl, cyc);
         }
         Rel<2 * W> p0, p1;
         split_key<W>(pk, p0, p1);
@@ -665,7 +679,7 @@ __global__ void __launch_bounds__(512) pb_expand_cta_kernel(const PbShard S) {
                 Key<W> child;
 #pragma unroll
                 for (int i = 0; i < 2 * W; ++i) child.k[i] = 0;
-                if (valid && a != back) {
+                if (valid && !((skip >> a) & 1u)) {
                     bool co;
                     const int stt = apply_move<2 * W, TRUSTED>(r0, r1, a, mrl, cyc, co);
                     if (stt != ST_OK) {
