@@ -2,6 +2,7 @@
 // Host-side runtime only: argument checks, the context (streams + grow-only scratch) and
 // the chunked H2D -> kernel -> D2H pipelines behind the *_host entry points.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -31,6 +32,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 constexpr int kStreams = 3;
 constexpr int64_t kChunkRows = 1 << 17;  // rows per pipeline chunk of the *_host calls
+constexpr int64_t kEnvChunkRows = 1 << 18;  // acs_env_step_host: 4 chunks per 1 Mi rows (131072 .. 1048576 measure the same at N = 1)
 constexpr size_t kSmallCall = 64 * 1024;   // single-call API: everything goes through one pinned staging buffer
 
 struct Scratch {
@@ -371,7 +373,12 @@ int acs_env_step_host(acs_ctx* c, int8_t* d_state, int32_t* d_step_count, const 
     // done, and the per-row scalars (reward, done, truncated) live in one whole-call buffer and come
     // back in three large copies behind the last observation chunk -- 11 device-to-host copies per
     // 1 Mi rows instead of 32, no synchronisation before the final one.
-    const int64_t chunk = n < kChunkRows ? (n > 0 ? n : 1) : kChunkRows;
+    static const int64_t chunk_rows = [] {  // ACS_HOST_CHUNK_ROWS: rows per pipeline chunk of this call (multiple of 128)
+        const char* e = std::getenv("ACS_HOST_CHUNK_ROWS");
+        const long long v = e ? std::atoll(e) : 0;
+        return (v >= 128 && v % 128 == 0) ? (int64_t)v : kEnvChunkRows;
+    }();
+    const int64_t chunk = n < chunk_rows ? (n > 0 ? n : 1) : chunk_rows;
     const size_t o_rew = align_up((size_t)n, 256);
     const size_t o_done = o_rew + align_up((size_t)n * 4, 256);
     const size_t o_tr = o_done + align_up((size_t)n, 256);
