@@ -160,7 +160,7 @@ def test_full_size_properties():
     assert np.array_equal(c2[ok], S[ok])
 
 
-@pytest.mark.parametrize("n,steps", [(5000, 60), (300_001, 4)])  # the second spans 3 pipeline chunks
+@pytest.mark.parametrize("n,steps", [(5000, 60), (600_001, 3)])  # the second spans 3 pipeline chunks (262 144 rows each)
 def test_env_step_batch_vs_oracle(n, steps):
     """acs_env_step_host (device-resident state, host actions in, host results out, chunked
     copy/compute pipeline) == oracle ACEnv.step."""
