@@ -96,3 +96,22 @@ def test_restatement_reproduces_the_reference_training_run(golden, name):
         exp = golden["train"][name]["params"][k]
         got = [float(v.double().sum()), float(v.double().abs().sum()), float(v.flatten()[0])]
         np.testing.assert_allclose(got, exp, rtol=2e-5, atol=2e-6, err_msg=f"{name}: {k}")
+
+
+def test_no_cpu_fallback_in_the_training_path():
+    """The device-resident loop and its kernels refuse to run without CUDA instead of falling back."""
+    import argparse
+
+    from ac_solver_b200 import _lib
+    from ac_solver_b200.agents.training import gae, ppo_training_loop
+
+    with pytest.raises(_lib.AcsError):
+        ppo_training_loop(None, argparse.Namespace(), "cpu", None, None, [], {}, {}, set(), [])
+    x = torch.zeros(4, 3)
+    with pytest.raises(AssertionError):
+        gae(x, x, x, torch.zeros(3), torch.zeros(3), 0.99, 0.95)
+    if not torch.cuda.is_available():
+        from ac_solver_b200.agents.ppo import train_ppo
+
+        with pytest.raises(RuntimeError):
+            train_ppo(["--num-envs", "2", "--num-steps", "4"])
