@@ -171,6 +171,49 @@ def _py_worker(job):
     return n, time.perf_counter() - t0
 
 
+def _py_greedy_worker(job):
+    """The reference's own greedy_search (baseline/_ref) on one presentation at a small budget."""
+    import contextlib
+    import io
+
+    pres, budget = job
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    from ac_solver.search.greedy import greedy_search as ref_greedy
+
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_greedy(np.array(pres), max_nodes_to_explore=budget)
+    return time.perf_counter() - t0
+
+
+def _py_bfs_worker(job):
+    """The reference's own bfs (baseline/_ref) on one presentation; returns seconds (one core)."""
+    import contextlib
+    import io
+
+    pres, budget = job
+    sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+    from ac_solver.search.breadth_first import bfs as ref_bfs
+
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_bfs(np.array(pres), max_nodes_to_explore=budget)
+    return time.perf_counter() - t0
+
+
+def python_pool_map(fn, jobs, procs, timeout=180.0):
+    """Run fn over jobs in fresh interpreters (spawn); None if the staged reference is missing or anything fails."""
+    if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "ac_solver")):
+        return None
+    import multiprocessing as mp
+
+    try:
+        with mp.get_context("spawn").Pool(max(1, min(procs, len(jobs)))) as pool:
+            return pool.map_async(fn, jobs).get(timeout=timeout)  # bounded: an auxiliary baseline must never hang the bench
+    except Exception:
+        return None
+
+
 def cpu_baseline_python(rows, mrl, seconds=8.0):
     """The reference's own pure-Python ACMove on every host core, bounded sample."""
     if not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "ac_solver")):
@@ -711,6 +754,16 @@ def bench_bfs(args, world=1, dist=None):
         cpu_s = time.perf_counter() - c0
         out["cpu_baseline"] = {"value": cinfo["n_expanded"] / cpu_s, "unit": "nodes expanded/s", "cores": 1, "kind": "port",
                                "sample": "C oracle bfs, same presentation, budget 2e6 (sequential algorithm, one core)"}
+        if not getattr(args, "skip_python_baseline", False):
+            # the reference's own bfs on AK(3) at budget 1e5, one core
+            pyb = 100_000
+            secs = python_pool_map(_py_bfs_worker, [(AK3.tolist(), pyb)], 1)
+            if secs:
+                _, _, pinfo = O.bfs(AK3, pyb)  # the same run through the oracle: how many nodes that budget expands
+                out["cpu_baseline_python"] = {"value": pinfo["n_expanded"] / secs[0], "unit": "nodes expanded/s", "cores": 1,
+                                              "kind": "reference", "visited_per_s": pinfo["n_visited"] / secs[0],
+                                              "sample": f"the reference's own bfs (baseline/_ref, pure Python) on AK(3) at budget {pyb}: "
+                                                        f"{secs[0]:.1f} s on one core, {pinfo['n_expanded']} nodes expanded"}
     return out
 
 
@@ -789,6 +842,21 @@ def bench_greedy(args, world=1, dist=None):
                                "sample": f"C oracle greedy_search on {len(sample)} of the {len(unsolved)} unsolved rows at budget "
                                          f"{budget}, one search per thread on {cores} threads: {cs:.1f} s; the 533 solved rows are cheap",
                                "speedup_vs_allcore_port_wall": est / wall, "speedup_vs_allcore_port_device": est / dev_s}
+        if not getattr(args, "skip_python_baseline", False):
+            # the reference's own greedy_search on 16 sampled unsolved rows at budget 1e4,
+            # spread over the host cores, extrapolated linearly in the budget to 1e6 x 657 unsolved rows
+            pyb = 10_000
+            psample = unsolved[:: max(1, len(unsolved) // 16)][:16]
+            p0 = time.perf_counter()
+            secs = python_pool_map(_py_greedy_worker, [(pres[k].tolist(), pyb) for k in psample], cores)
+            if secs:
+                per_row = sum(secs) / len(secs) * (budget / pyb)
+                out["cpu_baseline_python"] = {
+                    "value": per_row * len(unsolved) / cores, "unit": "s (extrapolated sweep, all cores)", "cores": cores, "kind": "reference",
+                    "core_seconds_per_unsolved_row_at_budget": per_row,
+                    "sample": f"the reference's own greedy_search (baseline/_ref) on {len(psample)} unsolved rows at budget {pyb}: "
+                              f"{sum(secs) / len(secs):.2f} core-s per row ({time.perf_counter() - p0:.1f} s wall on {cores} cores); "
+                              f"EXTRAPOLATED x{budget // pyb} in the budget and to the {len(unsolved)} unsolved rows"}
     return out
 
 
