@@ -239,7 +239,11 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
         except ImportError:
             pass
     log = {}
+    update_seconds = []  # wall time of every whole iteration (rollout + GAE + updates + logging), for benchmarks
+    import time as _time
+
     for update in it:
+        _t0 = _time.perf_counter()
         random.seed(args.seed + update)
         np.random.seed(args.seed + update)
         if not (use_graphs):  # a captured graph owns its RNG offsets; reseeding would not reach it
@@ -310,6 +314,8 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
             log["charts/unsolved"] = envs._curriculum["n_states"] - c["n_solved"]
         if wandb is not None:
             wandb.log(log)
+        update_seconds.append(_time.perf_counter() - _t0)  # (the logging above read device scalars: the update is complete)
+        log["perf/update_seconds"] = list(update_seconds)
 
         if checkpoint_every and update % checkpoint_every == 0:
             sync_curriculum(envs, curr_states, success_record, ACMoves_hist, states_processed)

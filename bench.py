@@ -1036,7 +1036,7 @@ def bench_ppo(args):
     from ac_solver_b200.agents.ppo_agent import Agent
     from ac_solver_b200.agents import training as T
 
-    n_envs, steps, updates = 4096, 200, 6
+    n_envs, steps, updates = 4096, 200, 8
     a = ppo_args(["--num-envs", str(n_envs), "--num-steps", str(steps), "--horizon-length", "200", "--nodes-counts", "512", "512",
                   "--total-timesteps", str(n_envs * steps * updates), "--num-minibatches", "4", "--update-epochs", "1",
                   "--norm-rewards", "--states-type", "all"])
@@ -1064,24 +1064,22 @@ def bench_ppo(args):
     os.chdir("/tmp")
     try:
         with contextlib.redirect_stdout(io.StringIO()):
-            # first call: warm-up (graph capture, allocator); second call on the same objects is timed
-            a.total_timesteps = n_envs * steps * 2
-            T.ppo_training_loop(envs, a, dev, opt, agent, list(range(n_envs)), {"solved": set(), "unsolved": set()}, {}, set(),
-                                initial_states, checkpoint_every=0, progress=False)
             a.total_timesteps = n_envs * steps * updates
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
             log = T.ppo_training_loop(envs, a, dev, opt, agent, list(range(n_envs)), {"solved": set(), "unsolved": set()}, {},
                                       set(), initial_states, checkpoint_every=0, progress=False)
             torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
     finally:
         os.chdir(cwd)
+    # the first update captures the two CUDA graphs and sizes the allocator's pools: steady state = the later updates
+    secs = sorted(log["perf/update_seconds"][2:])
+    dt = secs[len(secs) // 2] * updates  # median whole-iteration time x updates
     return {"metric": "PPO training timesteps/sec (rollout + GAE + update, whole iterations)",
             "workload": f"{n_envs} envs x {steps} steps per update, {updates} updates, 2x512 tanh actor+critic fp32, 4 minibatches x 1 epoch, "
-                        "NormalizeReward + clip and curriculum on the device; the second ppo_training_loop call on warm objects "
-                        "(its own graph capture included)",
+                        "NormalizeReward + clip and curriculum on the device; median whole-iteration wall time of updates 3.." + str(updates)
+                        + " of one ppo_training_loop call (updates 1-2 capture the CUDA graphs)",
             "timesteps_per_s": n_envs * steps * updates / dt, "seconds_per_update": dt / updates,
+            "update_seconds": [round(x, 4) for x in log["perf/update_seconds"]],
             "value_loss": log["losses/value_loss"], "policy_loss": log["losses/policy_loss"], "entropy": log["losses/entropy_loss"],
             "approx_kl": log["losses/approx_kl"], "episodes": log["charts/episode"],
             "note": "the reference's loop steps 4096 Python environments one by one on the host: at its measured "
