@@ -17,7 +17,6 @@ The host sees one scalar per epoch (approx_kl for the early stop) and a handful 
 
 from __future__ import annotations
 
-import ctypes as C
 import math
 import os
 import random

@@ -1,4 +1,4 @@
-import sys, json, argparse
+import sys, argparse
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 a = argparse.Namespace(greedy_budget=1_000_000)
