@@ -123,6 +123,9 @@ _SIGS = {
     "acs_ppo_loss_workspace_bytes": (C.c_int, []),
     "acs_ppo_loss": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_double, C.c_double, C.c_double, _P]),
+    "acs_rollout_sample_record": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                            C.c_uint64, _P]),
+    "acs_rollout_finish": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int, _P]),
     "acs_ball_sizes": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
     "acs_pbfs_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int64, C.POINTER(_P)]),
     "acs_pbfs_export": (C.c_int, [_P, _P]),

@@ -128,7 +128,7 @@ def sync_curriculum(envs, curr_states, success_record, ACMoves_hist, states_proc
 
 
 def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success_record, ACMoves_hist, states_processed,
-                      initial_states, use_graphs=True, checkpoint_every=100, progress=True):
+                      initial_states, use_graphs=True, checkpoint_every=100, progress=True, fused_rollout=True):
     dev = torch.device(device)
     if dev.type != "cuda":
         raise _lib.AcsError("ppo_training_loop runs on a CUDA device only (there is no CPU fallback)")
@@ -142,14 +142,20 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
     values = torch.zeros((T, N), device=dev)
     advantages = torch.zeros((T, N), device=dev)
     returns = torch.zeros((T, N), device=dev)
-    t_idx = torch.zeros(1, dtype=torch.int64, device=dev)
+    ctr = torch.zeros(2, dtype=torch.int64, device=dev)  # {time index of the rollout, draw counter of the sampler}
+    t_idx = ctr[0:1]
     next_done = torch.zeros(N, device=dev)
     ep_return = torch.zeros(N, device=dev)
     ep_length = torch.zeros(N, device=dev)
-    ring_ret = torch.zeros(101, device=dev)  # the reference's deque(maxlen=100) of episodic returns / lengths (+1 dump slot)
+    # the reference's deque([0], maxlen=100) of episodic returns / lengths: slot 0 holds the initial 0, ring_n counts
+    # the entries ever appended (initial one included); slot 100 is the dump slot of the torch-op path
+    ring_ret = torch.zeros(101, device=dev)
     ring_len = torch.zeros(101, device=dev)
-    ring_n = torch.zeros(1, dtype=torch.int64, device=dev)
-    episodes = torch.zeros(1, dtype=torch.int64, device=dev)
+    ring_n = torch.ones(1, dtype=torch.int64, device=dev)
+    action_u8 = torch.zeros(N, dtype=torch.uint8, device=dev)
+    n_actions = int(envs.single_action_space.n)
+    fused_rollout = bool(fused_rollout) and n_actions <= 16
+    L = _lib.lib()
     transform = envs.norm_rewards or envs.clip_rewards is not None
 
     envs.reset()
@@ -166,6 +172,24 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
         wandb.init(project=args.wandb_project_name, name=run_name, config=vars(args), save_code=True)
 
     # ---- one vector step of the rollout, sync-free (graph) --------------------------------------
+    def rollout_step_fused():
+        # policy forward (cuBLAS) + TWO bookkeeping kernels around the environment step (csrc/ppo_kernels.cu)
+        with torch.no_grad():
+            state = envs.state
+            logits, value = agent(state.float())
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(L.acs_rollout_sample_record(
+                state.data_ptr(), next_done.data_ptr(), logits.data_ptr(), value.data_ptr(), ctr.data_ptr(), obs.data_ptr(),
+                dones.data_ptr(), values.data_ptr(), logprobs.data_ptr(), actions.data_ptr(), action_u8.data_ptr(), N, T, width,
+                n_actions, int(args.seed) & (2 ** 64 - 1), stream))
+            envs.step_device(action_u8)
+            r = envs.transformed_reward() if transform else envs.reward.float()
+            _lib.check(L.acs_rollout_finish(
+                r.data_ptr(), envs.done.data_ptr(), envs.truncated.data_ptr(), ctr.data_ptr(), rewards.data_ptr(),
+                next_done.data_ptr(), ep_return.data_ptr(), ep_length.data_ptr(), ring_ret.data_ptr(), ring_len.data_ptr(),
+                ring_n.data_ptr(), N, T, 100, stream))
+            ctr.add_(1)
+
     def rollout_step():
         with torch.no_grad():
             state = envs.state
@@ -187,14 +211,12 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
             slot = torch.where(fin, pos, torch.full_like(pos, 100))
             ring_ret.scatter_(0, slot, ep_return)
             ring_len.scatter_(0, slot, ep_length)
-            nfin = fin.sum()
-            ring_n.add_(nfin)
-            episodes.add_(nfin)
+            ring_n.add_(fin.sum())
             ep_return.masked_fill_(fin, 0.0)
             ep_length.masked_fill_(fin, 0.0)
-            t_idx.add_(1)
+            ctr.add_(1)
 
-    rollout = _Graphed(rollout_step, warm=3, enabled=use_graphs)
+    rollout = _Graphed(rollout_step_fused if fused_rollout else rollout_step, warm=3, enabled=use_graphs)
 
     # ---- one minibatch update (graph) -----------------------------------------------------------
     mb = args.minibatch_size
@@ -294,14 +316,14 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
         y_pred, y_true = flat["values"], flat["returns"]
         var_y = torch.var(y_true, unbiased=False)
         ev = float("nan") if float(var_y) == 0 else float(1 - torch.var(y_true - y_pred, unbiased=False) / var_y)
-        k = int(min(int(ring_n), 100))
-        rets = ring_ret[:k].cpu().numpy() if k else np.array([0.0])
-        lens = ring_len[:k].cpu().numpy() if k else np.array([0.0])
+        n_episodes = int(ring_n) - 1
+        k = min(n_episodes + 1, 100)
+        rets, lens = ring_ret[:k].cpu().numpy(), ring_len[:k].cpu().numpy()
         if not args.norm_rewards:
             rets, lens = rets / envs.max_reward, lens / args.horizon_length
         ls = last_stats.cpu().numpy()
         lr_now = optimizer.param_groups[0]["lr"]
-        log = {"charts/global_step": global_step, "charts/episode": int(episodes),
+        log = {"charts/global_step": global_step, "charts/episode": n_episodes,
                "charts/normalized_returns_mean": float(rets.mean()), "charts/normalized_lengths_mean": float(lens.mean()),
                "charts/learning_rate": float(lr_now), "losses/value_loss": float(ls[2]), "losses/policy_loss": float(ls[1]),
                "losses/entropy_loss": float(ls[3]), "losses/approx_kl": float(ls[4]), "losses/explained_variance": ev,
@@ -320,7 +342,7 @@ def ppo_training_loop(envs, args, device, optimizer, agent, curr_states, success
             sync_curriculum(envs, curr_states, success_record, ACMoves_hist, states_processed)
             os.makedirs(out_dir, exist_ok=True)
             torch.save({"critic": agent.critic.state_dict(), "actor": agent.actor.state_dict(),
-                        "optimizer": optimizer.state_dict(), "update": update, "episode": int(episodes),
+                        "optimizer": optimizer.state_dict(), "update": update, "episode": n_episodes,
                         "config": vars(args), "mean_return": float(rets.mean()), "success_record": success_record,
                         "value_loss": float(ls[2]), "policy_loss": float(ls[1]), "entropy_loss": float(ls[3]),
                         "approx_kl": float(ls[4]), "explained_var": ev, "clipfrac": log["losses/clipfrac"],

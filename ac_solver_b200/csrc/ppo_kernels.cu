@@ -286,3 +286,206 @@ int acs_ppo_loss(const float* d_logits, const float* d_newvalue, const int64_t* 
 }
 
 }  // extern "C"
+
+// ---- rollout bookkeeping of the PPO loop, fused (agents/training.py:139-228 of the reference) ------------
+// The reference's rollout step is a dozen small tensor writes around the policy and the environment
+// (obs[step] = next_obs, dones[step] = next_done, values / actions / logprobs[step], rewards[step],
+// episodic return / length bookkeeping, the deque of finished episodes).  On the device each of them is a
+// kernel launch of a few microseconds inside the rollout graph; here they are two kernels:
+//   sample_record (before the env step): Categorical sampling by the Gumbel-max trick from a counter-based
+//       generator, log-probability of the drawn action, and the writes into the [T, N] buffers at time t;
+//   finish (after the env step and the reward wrappers): rewards[t], next_done, episodic statistics.
+namespace acs {
+
+__device__ __forceinline__ unsigned long long rl_mix(unsigned long long x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+struct RolloutRecordParams {
+    const int8_t* state;       // [N, width] current observations
+    const float* next_done;    // [N]
+    const float* logits;       // [N, A]
+    const float* value;        // [N]
+    const long long* ctr;      // device scalars {t, draw counter}
+    int8_t* obs_buf;           // [T, N, width]
+    float* dones_buf;          // [T, N]
+    float* values_buf;         // [T, N]
+    float* logprobs_buf;       // [T, N]
+    long long* actions_buf;    // [T, N]
+    uint8_t* action_u8;        // [N]  the drawn actions for the environment kernel
+    long long N, T;
+    int width, A;
+    unsigned long long seed;
+};
+
+__global__ void __launch_bounds__(256) rollout_sample_record_kernel(const RolloutRecordParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const long long t = P.ctr[0], draw = P.ctr[1];
+    if (t < 0 || t >= P.T) return;  // the caller rolls out at most T steps between resets of the time index
+    const long long o = t * P.N + i;
+    // Categorical(logits).sample() as argmax(logits + Gumbel noise); log_prob of the drawn action
+    float zmax = -INFINITY, best = -INFINITY;
+    int a = 0;
+    float z[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        z[k] = k < P.A ? P.logits[i * P.A + k] : -INFINITY;
+        zmax = fmaxf(zmax, z[k]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (k < P.A) {
+            se += __expf(z[k] - zmax);
+            const unsigned long long h = rl_mix(P.seed ^ rl_mix((unsigned long long)draw * 0x9E3779B97F4A7C15ull + (unsigned long long)i * 16ull + k));
+            const float u = ((float)(h >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+            const float g = z[k] - __logf(-__logf(u));
+            if (g > best) {
+                best = g;
+                a = k;
+            }
+        }
+    }
+    float za = z[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) za = (k == a) ? z[k] : za;
+    P.actions_buf[o] = a;
+    P.action_u8[i] = (uint8_t)a;
+    P.logprobs_buf[o] = za - (zmax + __logf(se));
+    P.values_buf[o] = P.value[i];
+    P.dones_buf[o] = P.next_done[i];
+    const int8_t* src = P.state + i * P.width;
+    int8_t* dst = P.obs_buf + o * P.width;
+    if ((P.width & 7) == 0) {
+        for (int k = 0; k < P.width / 8; ++k) reinterpret_cast<uint2*>(dst)[k] = reinterpret_cast<const uint2*>(src)[k];
+    } else {
+        for (int k = 0; k < P.width; ++k) dst[k] = src[k];
+    }
+}
+
+struct RolloutFinishParams {
+    const float* reward;       // [N] reward of the step as the loop receives it (after the wrappers)
+    const uint8_t* done;       // [N]
+    const uint8_t* truncated;  // [N]
+    const long long* ctr;      // {t, draw counter}
+    float* rewards_buf;        // [T, N]
+    float* next_done;          // [N]
+    float* ep_return;          // [N]
+    float* ep_length;          // [N]
+    float* ring_ret;           // [ring]  returns / lengths of the last `ring` finished episodes
+    float* ring_len;
+    unsigned long long* counters;  // {episodes finished}
+    long long N, T;
+    int ring;
+};
+
+__global__ void __launch_bounds__(256) rollout_finish_kernel(const RolloutFinishParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.N) return;
+    const long long t = P.ctr[0];
+    if (t < 0 || t >= P.T) return;
+    const float r = P.reward[i];
+    P.rewards_buf[t * P.N + i] = r;
+    const bool d = P.done[i] != 0;
+    P.next_done[i] = d ? 1.0f : 0.0f;  // torch.Tensor(done): terminated only (training.py:226-228)
+    const float er = P.ep_return[i] + r, el = P.ep_length[i] + 1.0f;
+    if (d || P.truncated[i]) {  // training.py:191-196: the episode's return and length enter the deque(maxlen=100)
+        const unsigned long long k = atomicAdd(&P.counters[0], 1ull);
+        P.ring_ret[k % (unsigned long long)P.ring] = er;
+        P.ring_len[k % (unsigned long long)P.ring] = el;
+        P.ep_return[i] = 0.f;
+        P.ep_length[i] = 0.f;
+    } else {
+        P.ep_return[i] = er;
+        P.ep_length[i] = el;
+    }
+}
+
+}  // namespace acs
+
+extern "C" {
+
+int acs_rollout_sample_record(const int8_t* d_state, const float* d_next_done, const float* d_logits, const float* d_value,
+                              const int64_t* d_ctr2, int8_t* d_obs_buf, float* d_dones_buf, float* d_values_buf,
+                              float* d_logprobs_buf, int64_t* d_actions_buf, uint8_t* d_action_u8, int64_t N, int64_t T, int width,
+                              int n_actions, uint64_t seed, void* stream) {
+    if (N < 0 || T < 1 || width < 1 || n_actions < 1 || n_actions > 16) {
+        acs::set_last_error("rollout_sample_record: bad shape (1 <= n_actions <= 16)");
+        return ACS_ERR_INVALID;
+    }
+    if (N == 0) return ACS_OK;
+    if (!d_state || !d_next_done || !d_logits || !d_value || !d_ctr2 || !d_obs_buf || !d_dones_buf || !d_values_buf ||
+        !d_logprobs_buf || !d_actions_buf || !d_action_u8) {
+        acs::set_last_error("rollout_sample_record: null buffer");
+        return ACS_ERR_INVALID;
+    }
+    acs::RolloutRecordParams P{};
+    P.state = d_state;
+    P.next_done = d_next_done;
+    P.logits = d_logits;
+    P.value = d_value;
+    P.ctr = reinterpret_cast<const long long*>(d_ctr2);
+    P.obs_buf = d_obs_buf;
+    P.dones_buf = d_dones_buf;
+    P.values_buf = d_values_buf;
+    P.logprobs_buf = d_logprobs_buf;
+    P.actions_buf = reinterpret_cast<long long*>(d_actions_buf);
+    P.action_u8 = d_action_u8;
+    P.N = N;
+    P.T = T;
+    P.width = width;
+    P.A = n_actions;
+    P.seed = seed;
+    acs::rollout_sample_record_kernel<<<(unsigned)((N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        acs::set_last_error(cudaGetErrorString(e));
+        return ACS_ERR_CUDA;
+    }
+    return ACS_OK;
+}
+
+int acs_rollout_finish(const float* d_reward, const uint8_t* d_done, const uint8_t* d_truncated, const int64_t* d_ctr2,
+                       float* d_rewards_buf, float* d_next_done, float* d_ep_return, float* d_ep_length, float* d_ring_ret,
+                       float* d_ring_len, uint64_t* d_counters, int64_t N, int64_t T, int ring, void* stream) {
+    if (N < 0 || T < 1 || ring < 1) {
+        acs::set_last_error("rollout_finish: bad shape");
+        return ACS_ERR_INVALID;
+    }
+    if (N == 0) return ACS_OK;
+    if (!d_reward || !d_done || !d_truncated || !d_ctr2 || !d_rewards_buf || !d_next_done || !d_ep_return || !d_ep_length ||
+        !d_ring_ret || !d_ring_len || !d_counters) {
+        acs::set_last_error("rollout_finish: null buffer");
+        return ACS_ERR_INVALID;
+    }
+    acs::RolloutFinishParams P{};
+    P.reward = d_reward;
+    P.done = d_done;
+    P.truncated = d_truncated;
+    P.ctr = reinterpret_cast<const long long*>(d_ctr2);
+    P.rewards_buf = d_rewards_buf;
+    P.next_done = d_next_done;
+    P.ep_return = d_ep_return;
+    P.ep_length = d_ep_length;
+    P.ring_ret = d_ring_ret;
+    P.ring_len = d_ring_len;
+    P.counters = reinterpret_cast<unsigned long long*>(d_counters);
+    P.N = N;
+    P.T = T;
+    P.ring = ring;
+    acs::rollout_finish_kernel<<<(unsigned)((N + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        acs::set_last_error(cudaGetErrorString(e));
+        return ACS_ERR_CUDA;
+    }
+    return ACS_OK;
+}
+
+}  // extern "C"

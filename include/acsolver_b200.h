@@ -328,6 +328,23 @@ int acs_ppo_loss(const float *d_logits, const float *d_newvalue, const int64_t *
                  int norm_adv, int loss_clip, int clip_vloss, double clip_coef, double ent_coef, double vf_coef,
                  void *stream);
 
+/* Rollout bookkeeping of the PPO loop (agents/training.py:139-228 of the reference), two launches per vector step.
+ * d_ctr2 = device int64[2] {time index t, draw counter}; the caller resets t per update and adds 1 to both after every
+ * step (torch: ctr.add_(1)), so one captured CUDA graph serves every step.
+ * acs_rollout_sample_record: action ~ Categorical(logits) (Gumbel-max, counter-based generator keyed by seed, draw
+ *   counter, row), log-probability of the action, and obs[t] = state, dones[t] = next_done, values[t], actions[t],
+ *   logprobs[t]; d_action_u8 [N] feeds acs_vecenv_step.  1 <= n_actions <= 16.
+ * acs_rollout_finish (after the environment step and acs_reward_transform): rewards[t] = reward, next_done = done,
+ *   episodic return / length accumulation, and for finished episodes (done | truncated) an entry in the ring of the
+ *   last `ring` episodes (the reference's deque(maxlen=100)); d_counters[0] counts finished episodes. */
+int acs_rollout_sample_record(const int8_t *d_state, const float *d_next_done, const float *d_logits, const float *d_value,
+                              const int64_t *d_ctr2, int8_t *d_obs_buf, float *d_dones_buf, float *d_values_buf,
+                              float *d_logprobs_buf, int64_t *d_actions_buf, uint8_t *d_action_u8, int64_t N, int64_t T,
+                              int width, int n_actions, uint64_t seed, void *stream);
+int acs_rollout_finish(const float *d_reward, const uint8_t *d_done, const uint8_t *d_truncated, const int64_t *d_ctr2,
+                       float *d_rewards_buf, float *d_next_done, float *d_ep_return, float *d_ep_length, float *d_ring_ret,
+                       float *d_ring_len, uint64_t *d_counters, int64_t N, int64_t T, int ring, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

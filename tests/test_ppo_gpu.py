@@ -138,3 +138,106 @@ def test_graph_and_eager_updates_agree():
     torch.cuda.synchronize()
     for p, q in zip(nets[0].parameters(), nets[1].parameters()):
         assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+
+
+def test_fused_rollout_kernels():
+    """acs_rollout_sample_record / acs_rollout_finish (csrc/ppo_kernels.cu) against the torch ops they replace:
+    buffer writes at the device-resident time index, log-probabilities of the drawn actions, the action distribution
+    (chi-square against softmax), episodic statistics and the ring of finished episodes."""
+    from ac_solver_b200 import _lib
+
+    L = _lib.lib()
+    dev = torch.device("cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    N, T, W, A = 5000, 4, 72, 12
+    g = torch.Generator(device="cpu").manual_seed(0)
+    state = torch.randint(-2, 3, (N, W), generator=g, dtype=torch.int8).to(dev)
+    logits = (torch.randn(N, A, generator=g) * 1.5).to(dev)
+    value = torch.randn(N, generator=g).to(dev)
+    next_done = (torch.rand(N, generator=g) < 0.3).float().to(dev)
+    ctr = torch.tensor([2, 77], dtype=torch.int64, device=dev)
+    obs = torch.zeros((T, N, W), dtype=torch.int8, device=dev)
+    dones, values, logprobs = (torch.zeros((T, N), device=dev) for _ in range(3))
+    actions = torch.full((T, N), -1, dtype=torch.int64, device=dev)
+    a8 = torch.zeros(N, dtype=torch.uint8, device=dev)
+    _lib.check(L.acs_rollout_sample_record(state.data_ptr(), next_done.data_ptr(), logits.data_ptr(), value.data_ptr(), ctr.data_ptr(),
+                                           obs.data_ptr(), dones.data_ptr(), values.data_ptr(), logprobs.data_ptr(), actions.data_ptr(),
+                                           a8.data_ptr(), N, T, W, A, 1234, s))
+    torch.cuda.synchronize()
+    assert torch.equal(obs[2], state) and not obs[[0, 1, 3]].any()
+    assert torch.equal(dones[2], next_done) and torch.equal(values[2], value)
+    assert torch.equal(actions[2], a8.long()) and int(actions[2].min()) >= 0 and int(actions[2].max()) < A and (actions[[0, 1, 3]] == -1).all()
+    ref_lp = torch.log_softmax(logits, -1).gather(1, actions[2][:, None]).squeeze(1)
+    np.testing.assert_allclose(logprobs[2].cpu().numpy(), ref_lp.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    # same (seed, draw counter) -> same draws; another draw counter -> other draws
+    act2 = torch.zeros_like(actions)
+    _lib.check(L.acs_rollout_sample_record(state.data_ptr(), next_done.data_ptr(), logits.data_ptr(), value.data_ptr(), ctr.data_ptr(),
+                                           obs.data_ptr(), dones.data_ptr(), values.data_ptr(), logprobs.data_ptr(), act2.data_ptr(),
+                                           a8.data_ptr(), N, T, W, A, 1234, s))
+    assert torch.equal(act2[2], actions[2])
+    ctr[1] = 78
+    _lib.check(L.acs_rollout_sample_record(state.data_ptr(), next_done.data_ptr(), logits.data_ptr(), value.data_ptr(), ctr.data_ptr(),
+                                           obs.data_ptr(), dones.data_ptr(), values.data_ptr(), logprobs.data_ptr(), act2.data_ptr(),
+                                           a8.data_ptr(), N, T, W, A, 1234, s))
+    assert (act2[2] != actions[2]).float().mean() > 0.3
+    # distribution: one logits row replicated 400 000 times, chi-square with 11 degrees of freedom (99.9 % quantile: 31.3)
+    M = 400_000
+    row = torch.tensor([0.3, -1.0, 2.0, 0.0, 0.5, -2.5, 1.0, 0.1, -0.4, 0.9, -3.0, 0.2])
+    big = row.repeat(M, 1).to(dev)
+    bobs = torch.zeros((1, M, 8), dtype=torch.int8, device=dev)
+    bz = torch.zeros((1, M), device=dev)
+    bact = torch.zeros((1, M), dtype=torch.int64, device=dev)
+    c0 = torch.tensor([0, 5], dtype=torch.int64, device=dev)
+    _lib.check(L.acs_rollout_sample_record(bobs.data_ptr(), bz.data_ptr(), big.data_ptr(), bz.data_ptr(), c0.data_ptr(), bobs.data_ptr(),
+                                           bz.clone().data_ptr(), bz.clone().data_ptr(), bz.clone().data_ptr(), bact.data_ptr(),
+                                           torch.zeros(M, dtype=torch.uint8, device=dev).data_ptr(), M, 1, 8, A, 99, s))
+    counts = torch.bincount(bact[0], minlength=A).double().cpu().numpy()
+    p = torch.softmax(row.double(), 0).numpy()
+    chi2 = float(((counts - M * p) ** 2 / (M * p)).sum())
+    assert chi2 < 40.0, chi2
+
+    # ---- finish: rewards[t], next_done, episodic statistics, ring of finished episodes ----
+    r = torch.randn(N, generator=g).to(dev)
+    done = (torch.rand(N, generator=g) < 0.01).to(torch.uint8).to(dev)
+    trunc = (torch.rand(N, generator=g) < 0.01).to(torch.uint8).to(dev)
+    rewards = torch.zeros((T, N), device=dev)
+    nd = torch.zeros(N, device=dev)
+    ep_r, ep_l = torch.randn(N, generator=g).to(dev), torch.randint(0, 50, (N,), generator=g).float().to(dev)
+    ep_r0, ep_l0 = ep_r.clone(), ep_l.clone()
+    ring_r, ring_l = torch.zeros(101, device=dev), torch.zeros(101, device=dev)
+    ring_n = torch.ones(1, dtype=torch.int64, device=dev)
+    ctr = torch.tensor([1, 0], dtype=torch.int64, device=dev)
+    _lib.check(L.acs_rollout_finish(r.data_ptr(), done.data_ptr(), trunc.data_ptr(), ctr.data_ptr(), rewards.data_ptr(), nd.data_ptr(),
+                                    ep_r.data_ptr(), ep_l.data_ptr(), ring_r.data_ptr(), ring_l.data_ptr(), ring_n.data_ptr(), N, T, 100, s))
+    torch.cuda.synchronize()
+    fin = (done | trunc).bool()
+    assert torch.equal(rewards[1], r) and not rewards[[0, 2, 3]].any() and torch.equal(nd, done.float())
+    assert torch.equal(ep_r[~fin], (ep_r0 + r)[~fin]) and torch.equal(ep_l[~fin], (ep_l0 + 1)[~fin])
+    assert not ep_r[fin].any() and not ep_l[fin].any()
+    nf = int(fin.sum())
+    assert int(ring_n) == 1 + nf and 0 < nf < 100
+    got = sorted(zip(ring_r[1 : 1 + nf].cpu().tolist(), ring_l[1 : 1 + nf].cpu().tolist()))
+    exp = sorted(zip((ep_r0 + r)[fin].cpu().tolist(), (ep_l0 + 1)[fin].cpu().tolist()))
+    assert got == exp and float(ring_r[0]) == 0.0
+
+
+def test_fused_and_torch_rollout_paths_train():
+    """The loop with the two bookkeeping kernels and the loop with the torch ops they replace both train (same
+    algorithm, different random streams): finite losses, identical bookkeeping invariants."""
+    from ac_solver_b200.agents.environment import get_env
+    from ac_solver_b200.agents.ppo_agent import Agent
+    from ac_solver_b200.agents.training import ppo_training_loop
+
+    for fused in (True, False):
+        a = _tiny_args()
+        torch.manual_seed(0)
+        envs, initial_states, curr, rec, hist, processed = get_env(a)
+        dev = torch.device("cuda")
+        agent = Agent(envs, a.nodes_counts).to(dev)
+        opt = torch.optim.Adam(agent.parameters(), lr=torch.tensor(a.learning_rate, device=dev), eps=a.epsilon, capturable=True)
+        log = ppo_training_loop(envs, a, dev, opt, agent, curr, rec, hist, processed, initial_states, checkpoint_every=0,
+                                progress=False, fused_rollout=fused)
+        assert np.isfinite(log["losses/value_loss"]) and log["charts/global_step"] == 64 * 32 * 6
+        assert log["charts/episode"] >= 64 and 0 < log["losses/entropy_loss"] <= np.log(12) + 1e-4
+        # every finished episode was truncated at the horizon (24) or solved earlier: mean length <= horizon
+        assert 0 < log["charts/normalized_lengths_mean"] <= 1.0 + 1e-6
