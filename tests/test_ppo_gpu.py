@@ -168,7 +168,7 @@ def test_fused_rollout_kernels():
     assert torch.equal(dones[2], next_done) and torch.equal(values[2], value)
     assert torch.equal(actions[2], a8.long()) and int(actions[2].min()) >= 0 and int(actions[2].max()) < A and (actions[[0, 1, 3]] == -1).all()
     ref_lp = torch.log_softmax(logits, -1).gather(1, actions[2][:, None]).squeeze(1)
-    np.testing.assert_allclose(logprobs[2].cpu().numpy(), ref_lp.cpu().numpy(), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(logprobs[2].cpu().numpy(), ref_lp.cpu().numpy(), rtol=1e-5, atol=1e-5)  # fast exp / log
     # same (seed, draw counter) -> same draws; another draw counter -> other draws
     act2 = torch.zeros_like(actions)
     _lib.check(L.acs_rollout_sample_record(state.data_ptr(), next_done.data_ptr(), logits.data_ptr(), value.data_ptr(), ctr.data_ptr(),
@@ -188,9 +188,10 @@ def test_fused_rollout_kernels():
     bz = torch.zeros((1, M), device=dev)
     bact = torch.zeros((1, M), dtype=torch.int64, device=dev)
     c0 = torch.tensor([0, 5], dtype=torch.int64, device=dev)
-    _lib.check(L.acs_rollout_sample_record(bobs.data_ptr(), bz.data_ptr(), big.data_ptr(), bz.data_ptr(), c0.data_ptr(), bobs.data_ptr(),
-                                           bz.clone().data_ptr(), bz.clone().data_ptr(), bz.clone().data_ptr(), bact.data_ptr(),
-                                           torch.zeros(M, dtype=torch.uint8, device=dev).data_ptr(), M, 1, 8, A, 99, s))
+    bd, bv, bl, b8 = bz.clone(), bz.clone(), bz.clone(), torch.zeros(M, dtype=torch.uint8, device=dev)
+    bstate = torch.zeros((M, 8), dtype=torch.int8, device=dev)
+    _lib.check(L.acs_rollout_sample_record(bstate.data_ptr(), bz.data_ptr(), big.data_ptr(), bz.data_ptr(), c0.data_ptr(), bobs.data_ptr(),
+                                           bd.data_ptr(), bv.data_ptr(), bl.data_ptr(), bact.data_ptr(), b8.data_ptr(), M, 1, 8, A, 99, s))
     counts = torch.bincount(bact[0], minlength=A).double().cpu().numpy()
     p = torch.softmax(row.double(), 0).numpy()
     chi2 = float(((counts - M * p) ** 2 / (M * p)).sum())
@@ -198,8 +199,8 @@ def test_fused_rollout_kernels():
 
     # ---- finish: rewards[t], next_done, episodic statistics, ring of finished episodes ----
     r = torch.randn(N, generator=g).to(dev)
-    done = (torch.rand(N, generator=g) < 0.01).to(torch.uint8).to(dev)
-    trunc = (torch.rand(N, generator=g) < 0.01).to(torch.uint8).to(dev)
+    done = (torch.rand(N, generator=g) < 0.005).to(torch.uint8).to(dev)
+    trunc = (torch.rand(N, generator=g) < 0.005).to(torch.uint8).to(dev)
     rewards = torch.zeros((T, N), device=dev)
     nd = torch.zeros(N, device=dev)
     ep_r, ep_l = torch.randn(N, generator=g).to(dev), torch.randint(0, 50, (N,), generator=g).float().to(dev)
