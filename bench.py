@@ -887,11 +887,28 @@ def bench_vecenv(args):
     actor = torch.nn.Sequential(torch.nn.Linear(72, 512), torch.nn.Tanh(), torch.nn.Linear(512, 512), torch.nn.Tanh(),
                                 torch.nn.Linear(512, 12)).cuda()
 
+    from ac_solver_b200 import _lib as _L
+
+    lib = _L.lib()
+    dev = env.dev
+    # Categorical sampling (Gumbel-max) + the rollout record of one step in ONE kernel (csrc/ppo_kernels.cu), as in
+    # agents/training.py; the record buffers hold a single time slot here
+    ctr = torch.zeros(2, dtype=torch.int64, device=dev)
+    rec_obs = torch.zeros((1, n_envs, 72), dtype=torch.int8, device=dev)
+    rec_f = [torch.zeros((1, n_envs), device=dev) for _ in range(3)]
+    rec_act = torch.zeros((1, n_envs), dtype=torch.int64, device=dev)
+    act8 = torch.zeros(n_envs, dtype=torch.uint8, device=dev)
+    zeros_n = torch.zeros(n_envs, device=dev)
+
     def rollout_step():
         with torch.no_grad():
             logits = actor(env.state.float())
-            g = -torch.log(-torch.log(torch.rand_like(logits).clamp_(1e-10, 1.0)))  # Gumbel-max == Categorical sampling
-            env.step_device((logits + g).argmax(dim=1))
+            _L.check(lib.acs_rollout_sample_record(
+                env.state.data_ptr(), zeros_n.data_ptr(), logits.data_ptr(), zeros_n.data_ptr(), ctr.data_ptr(), rec_obs.data_ptr(),
+                rec_f[0].data_ptr(), rec_f[1].data_ptr(), rec_f[2].data_ptr(), rec_act.data_ptr(), act8.data_ptr(), n_envs, 1, 72, 12, 7,
+                torch.cuda.current_stream(dev).cuda_stream))
+            ctr[1:2].add_(1)  # next draw; the time slot stays 0
+            env.step_device(act8)
             return env.transformed_reward()
 
     side = torch.cuda.Stream()
@@ -940,7 +957,7 @@ def bench_vecenv(args):
     c = env.curriculum_counters()
     out = {
         "metric": "PPO rollout env steps/sec (env side)", "workload": "BASELINE.json configs[3]: 4096 envs, horizon 200, "
-        "torch 2x512 actor on device, device-side NormalizeReward+clip and curriculum reset, one CUDA graph per vector step",
+        "torch 2x512 actor on device, fused sampling kernel, device-side NormalizeReward+clip and curriculum reset, one CUDA graph per vector step",
         "env_steps_per_s": n_envs * replays / (ms * 1e-3), "us_per_vector_step": 1e3 * ms / replays,
         "episodes_finished": c["episodes"], "states_solved": c["n_solved"], "host_syncs_per_step": 0,
         "env_only_steps_per_s": n_envs * replays / (ms_env * 1e-3), "env_only_us_per_vector_step": 1e3 * ms_env / replays,
