@@ -71,6 +71,64 @@ def greedy_search_batch(presentations, max_nodes_to_explore=10000, cyclically_re
     return out
 
 
+def greedy_search_groups(groups, max_nodes_to_explore=10000, cyclically_reduce_after_moves=False, device=None,
+                         path_cap=4096, threads=8):
+    """Sweep helper: ``groups`` is a list of presentation arrays [S_k, 2*mrl_k] (one array per max_relator_length).
+    All engines are CREATED first, then the groups search concurrently (one stream and one host thread each), then
+    the engines are destroyed -- ``cudaMalloc`` stalls behind kernels that are already running (measured: 0.02-1.5 s
+    per engine when interleaved with other groups' searches, 5 ms when not), so interleaving allocation and search
+    costs a sweep more than the searches themselves.  Returns a list (per group) of ``greedy_search_batch`` results."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    L = _lib.lib()
+    dev = _lib.default_device() if device is None else device
+    budget = int(max_nodes_to_explore)
+    arrays, handles = [], []
+    try:
+        for P in groups:
+            P8 = np.ascontiguousarray(np.asarray(P), dtype=np.int8)
+            if P8.ndim != 2 or P8.shape[1] % 2 or P8.shape[1] == 0:
+                raise ValueError("every group must be [S, 2*max_relator_length]")
+            if P8.size and np.abs(P8).max() > 2:
+                raise ValueError("the GPU search supports the two-generator alphabet {+-1, +-2} only")
+            h = C.c_void_p()
+            _lib.check(L.acs_greedy_create(dev, P8.shape[0], P8.shape[1] // 2, budget, int(bool(cyclically_reduce_after_moves)),
+                                           int(path_cap), C.byref(h)))
+            arrays.append(P8)
+            handles.append(h)
+
+        def run(k):
+            P8, h = arrays[k], handles[k]
+            S = P8.shape[0]
+            paths = np.zeros((S, path_cap, 2), np.int32)
+            res = (_lib.SearchResult * S)()
+            _lib.check(L.acs_greedy_run(h, P8.ctypes.data, paths.ctypes.data, res))
+            return paths, res
+
+        with ThreadPoolExecutor(max_workers=max(1, min(threads, len(arrays) or 1))) as pool:
+            raw = list(pool.map(run, range(len(arrays))))
+    finally:
+        for h in handles:
+            L.acs_greedy_destroy(h)
+    out = []
+    for k, (paths, res) in enumerate(raw):
+        S = arrays[k].shape[0]
+        if any(res[s].path_len > path_cap for s in range(S)):  # deeper than the buffer: redo this group with room
+            out.append(greedy_search_batch(arrays[k], budget, cyclically_reduce_after_moves, device=dev,
+                                           path_cap=int(max(res[s].path_len for s in range(S))) + 4))
+            continue
+        rows = []
+        for s in range(S):
+            r = res[s]
+            info = {"n_visited": int(r.n_visited), "n_expanded": int(r.n_expanded), "n_moves": int(r.n_moves),
+                    "frontier_left": int(r.frontier_left), "budget_hit": bool(r.budget_hit), "status": int(r.status),
+                    "minlen_log": [int(r.minlen_log[i]) for i in range(r.n_minlen)], "seconds_device": float(r.seconds_device),
+                    "rounds": int(r.n_levels)}
+            rows.append((bool(r.solved), [(int(a), int(l)) for a, l in paths[s, : r.path_len]], info))
+        out.append(rows)
+    return out
+
+
 def greedy_search(presentation, max_nodes_to_explore=10000, verbose=False, cyclically_reduce_after_moves=False):
     """search/greedy.py:15-121.
 

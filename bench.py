@@ -777,7 +777,7 @@ def bench_greedy(args, world=1, dist=None):
     from ast import literal_eval
     from concurrent.futures import ThreadPoolExecutor
 
-    from ac_solver_b200.search.greedy import greedy_search_batch
+    from ac_solver_b200.search.greedy import greedy_search_batch  # noqa: F401  (kept for interactive use)
 
     data = os.path.join(ROOT, "ac_solver_b200", "search", "miller_schupp", "data")
     with open(os.path.join(data, "all_presentations.txt")) as f:
@@ -791,19 +791,19 @@ def bench_greedy(args, world=1, dist=None):
         if k % world == rank:
             groups.setdefault(p.size, []).append(k)
 
-    def run_group(rows):
-        return rows, greedy_search_batch(np.stack([pres[k] for k in rows]), budget, path_cap=4096)
+    from ac_solver_b200.search.greedy import greedy_search_groups
 
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     mine, dev_s = {}, 0.0
-    with ThreadPoolExecutor(max_workers=8) as pool:  # the groups run concurrently (one stream each)
-        for rows, out in pool.map(run_group, list(groups.values())):
-            dev_s = max(dev_s, out[0][2]["seconds_device"])
-            for k, (solved, path, info) in zip(rows, out):
-                mine[k] = (solved, path, info["n_visited"], info["n_expanded"], info["rounds"])
+    group_rows = list(groups.values())
+    # engines are created first, then the length groups search concurrently (one stream each), see greedy_search_groups
+    for rows, out in zip(group_rows, greedy_search_groups([np.stack([pres[k] for k in rows]) for rows in group_rows], budget)):
+        dev_s = max(dev_s, out[0][2]["seconds_device"])
+        for k, (solved, path, info) in zip(rows, out):
+            mine[k] = (solved, path, info["n_visited"], info["n_expanded"], info["rounds"])
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     if dist is not None:

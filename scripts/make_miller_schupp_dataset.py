@@ -21,14 +21,13 @@ import json
 import os
 import sys
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from ac_solver_b200.search.breadth_first import bfs_device  # noqa: E402
-from ac_solver_b200.search.greedy import greedy_search_batch  # noqa: E402
+from ac_solver_b200.search.greedy import greedy_search_groups  # noqa: E402
 from ac_solver_b200.search.miller_schupp import (generate_miller_schupp_presentations,  # noqa: E402
                                                   write_list_to_text_file)
 
@@ -50,14 +49,12 @@ def main():
     for k, r in enumerate(rows):
         by_width.setdefault(len(r), []).append(k)
 
-    def run(ks):
-        return ks, greedy_search_batch(np.array([rows[k] for k in ks], dtype=np.int8), args.budget, path_cap=4096)
-
     result = {}
-    with ThreadPoolExecutor(max_workers=8) as pool:
-        for ks, out in pool.map(run, list(by_width.values())):
-            for k, (solved, path, info) in zip(ks, out):
-                result[k] = (solved, path)
+    key_lists = list(by_width.values())
+    outs = greedy_search_groups([np.array([rows[k] for k in ks], dtype=np.int8) for ks in key_lists], args.budget)
+    for ks, out in zip(key_lists, outs):
+        for k, (solved, path, info) in zip(ks, out):
+            result[k] = (solved, path)
     solved = [k for k in range(len(rows)) if result[k][0]]
     unsolved = [k for k in range(len(rows)) if not result[k][0]]
     ordered = solved + unsolved
